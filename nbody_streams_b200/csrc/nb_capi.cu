@@ -1,0 +1,301 @@
+// nb_capi.cu — extern "C" entry points of libnbody_sm100.so (see include/nbody_sm100.h).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "nb_dispatch.cuh"
+
+// launchers defined in nb_misc.cu / nb_ubench.cu
+int nb_launch_pack(int prec, int kernel_id, void* packed, long long first, const void* pos, int pos_dt,
+                   const void* mass, int mass_dt, double mass_scalar, const void* h, int h_dt, double h_scalar,
+                   long long n, long long n_pad, double eps2, cudaStream_t st);
+int nb_launch_finish(int prec, long long n_i, int grid, int IB, int n_sweeps, const int* n_jt, const void* ws,
+                     size_t slot_bytes, size_t part_off, double G, void* acc, void* phi, cudaStream_t st);
+int nb_launch_kick_drift_pack(int prec, double* pos, double* vel, const void* acc, int acc_dt,
+                              const double* acc_ext, void* packed, long long first, long long n, double dt_half,
+                              double dt, cudaStream_t st);
+int nb_launch_kick(double* vel, const void* acc, int acc_dt, const double* acc_ext, long long n, double dt_half,
+                   cudaStream_t st);
+size_t nb_energy_ws_bytes(long long n);
+int nb_launch_energy(const double* vel, const void* mass, int mass_dt, const void* phi, int phi_dt,
+                     const void* acc, int acc_dt, long long n, double* partials, double* out, cudaStream_t st);
+int nb_ubench_impl(int which, int iters, double* lane_ops_per_s, double* ms_out);
+
+using namespace nb;
+
+namespace {
+
+int g_variant_f32 = -1;   // -1: read NB_F32_VARIANT / NB_F64_VARIANT from the environment once
+int g_variant_f64 = -1;
+
+int env_variant(const char* name, int nmax) {
+    const char* s = std::getenv(name);
+    if (!s) return 0;
+    const int v = std::atoi(s);
+    return (v >= 0 && v < nmax) ? v : 0;
+}
+int cur_variant_f32() {
+    if (g_variant_f32 < 0) g_variant_f32 = env_variant("NB_F32_VARIANT", NV_F32);
+    return g_variant_f32;
+}
+int cur_variant_f64() {
+    if (g_variant_f64 < 0) g_variant_f64 = env_variant("NB_F64_VARIANT", NV_F64);
+    return g_variant_f64;
+}
+
+bool valid_prec(int p) { return p == NB_PREC_F32 || p == NB_PREC_F32_COMP || p == NB_PREC_F64; }
+bool valid_mode(int m) { return m == NB_MODE_FORCE || m == NB_MODE_POT || m == NB_MODE_BOTH; }
+bool valid_kid(int k) { return k >= 0 && k <= 4; }
+
+// tuning variants other than 0 exist only for plummer and spline
+int eff_variant(int prec, int kid) {
+    const bool allv = (kid == NB_KERNEL_PLUMMER || kid == NB_KERNEL_SPLINE);
+    if (!allv) return 0;
+    return prec == NB_PREC_F64 ? cur_variant_f64() : cur_variant_f32();
+}
+int block_i_for(int prec, int kid) {
+    const int v = eff_variant(prec, kid);
+    return prec == NB_PREC_F64 ? THREADS * variant_f64(v).ni : THREADS * 2 * variant_f32(v).np;
+}
+// workspace sizing must not depend on the softening kernel: use the largest i-block of the precision
+int block_i_max(int prec) {
+    int m = 0;
+    if (prec == NB_PREC_F64) {
+        for (int v = 0; v < NV_F64; ++v) m = max(m, THREADS * variant_f64(v).ni);
+    } else {
+        for (int v = 0; v < NV_F32; ++v) m = max(m, THREADS * 2 * variant_f32(v).np);
+    }
+    return m;
+}
+
+int dispatch(int prec, int kid, int mode, int op, const SweepArgs* a, int grid, int* out, cudaStream_t st) {
+    const int v = eff_variant(prec, kid);
+    if (prec == NB_PREC_F64) {
+        switch (kid) {
+            case 0: return nb_dispatch_f64_k0(mode, v, op, a, grid, out, st);
+            case 1: return nb_dispatch_f64_k1(mode, v, op, a, grid, out, st);
+            case 2: return nb_dispatch_f64_k2(mode, v, op, a, grid, out, st);
+            case 3: return nb_dispatch_f64_k3(mode, v, op, a, grid, out, st);
+            case 4: return nb_dispatch_f64_k4(mode, v, op, a, grid, out, st);
+        }
+    } else {
+        const int acc = (prec == NB_PREC_F32_COMP) ? 1 : 0;
+        switch (kid) {
+            case 0: return nb_dispatch_f32_k0(mode, acc, v, op, a, grid, out, st);
+            case 1: return nb_dispatch_f32_k1(mode, acc, v, op, a, grid, out, st);
+            case 2: return nb_dispatch_f32_k2(mode, acc, v, op, a, grid, out, st);
+            case 3: return nb_dispatch_f32_k3(mode, acc, v, op, a, grid, out, st);
+            case 4: return nb_dispatch_f32_k4(mode, acc, v, op, a, grid, out, st);
+        }
+    }
+    return NB_E_INVALID_ARG;
+}
+
+struct SlotLayout {
+    size_t full_bytes, part_off, slot_bytes;
+};
+SlotLayout slot_layout(int prec, long long n_i, int grid) {
+    const size_t eb = partial_elem_bytes(prec);
+    const size_t IBm = static_cast<size_t>(block_i_max(prec));
+    // full[] is indexed by ib*IB+li with the ACTUAL IB; rounding n_i up to the largest IB covers every variant
+    const size_t n_full = ((static_cast<size_t>(n_i) + IBm - 1) / IBm) * IBm;
+    SlotLayout L;
+    L.full_bytes = n_full * eb;
+    L.part_off   = (L.full_bytes + 255) & ~static_cast<size_t>(255);
+    L.slot_bytes = L.part_off + ((static_cast<size_t>(grid) * 2 * IBm * eb + 255) & ~static_cast<size_t>(255));
+    return L;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nb_version(void) { return 10000 * 0 + 100 * 1 + 0; }
+
+const char* nb_error_string(int err) {
+    if (err == 0) return "ok";
+    if (err > 0) return cudaGetErrorString(static_cast<cudaError_t>(err));
+    switch (err) {
+        case NB_E_INVALID_ARG: return "nbody_sm100: invalid argument";
+        case NB_E_WORKSPACE: return "nbody_sm100: workspace too small";
+        case NB_E_UNSUPPORTED: return "nbody_sm100: combination not compiled into this build";
+        case NB_E_ARCH: return "nbody_sm100: device is not sm_100 (B200)";
+    }
+    return "nbody_sm100: unknown error";
+}
+
+int nb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* mem_total, size_t* mem_free,
+                   int* clock_khz, char* name, int name_len) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) return (int)e;
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+        *clock_khz = khz;
+    }
+    if (mem_total || mem_free) {
+        size_t f = 0, t = 0;
+        e = cudaMemGetInfo(&f, &t);
+        if (e != cudaSuccess) return (int)e;
+        if (mem_total) *mem_total = t;
+        if (mem_free) *mem_free = f;
+    }
+    if (name && name_len > 0) {
+        std::strncpy(name, p.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return 0;
+}
+
+/* tuning (not part of the reference-facing surface): select a compiled variant */
+int nb_set_variant(int prec, int variant) {
+    if (prec == NB_PREC_F64) {
+        if (variant < 0 || variant >= NV_F64) return NB_E_INVALID_ARG;
+        g_variant_f64 = variant;
+    } else {
+        if (variant < 0 || variant >= NV_F32) return NB_E_INVALID_ARG;
+        g_variant_f32 = variant;
+    }
+    return 0;
+}
+int nb_get_variant(int prec) { return prec == NB_PREC_F64 ? cur_variant_f64() : cur_variant_f32(); }
+
+int nb_tile_j(void) { return TJ; }
+int nb_block_i(int prec) { return block_i_max(prec); }
+long nb_padded_count(long n) { return ((n + TJ - 1) / TJ) * TJ; }
+size_t nb_packed_bytes(int prec, long n) {
+    const size_t np = static_cast<size_t>(nb_padded_count(n));
+    return np * (prec == NB_PREC_F64 ? 40 : 20);
+}
+
+int nb_pack(int prec, int kernel_id, void* packed, long first, const void* pos, int pos_dt, const void* mass,
+            int mass_dt, double mass_scalar, const void* h, int h_dt, double h_scalar, long n, long n_pad,
+            double eps2, void* stream) {
+    if (!valid_prec(prec) || !valid_kid(kernel_id) || !packed || n < 0 || n_pad < n) return NB_E_INVALID_ARG;
+    if (first % TJ != 0 || n_pad % TJ != 0) return NB_E_INVALID_ARG;
+    if (n > 0 && !pos) return NB_E_INVALID_ARG;
+    return nb_launch_pack(prec, kernel_id, packed, first, pos, pos_dt, mass, mass_dt, mass_scalar, h, h_dt,
+                          h_scalar, n, n_pad, eps2, static_cast<cudaStream_t>(stream));
+}
+
+int nb_sweep_grid(int prec, int kernel_id, int mode, int* grid) {
+    if (!valid_prec(prec) || !valid_kid(kernel_id) || !valid_mode(mode) || !grid) return NB_E_INVALID_ARG;
+    int dev = 0, sms = 0, major = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return NB_E_ARCH;
+    int per_sm = 0;
+    const int rc = dispatch(prec, kernel_id, mode, OP_QUERY, nullptr, 0, &per_sm, 0);
+    if (rc) return rc;
+    if (per_sm < 1) per_sm = 1;
+    *grid = sms * per_sm;
+    return 0;
+}
+
+size_t nb_workspace_bytes(int prec, long n_i, int grid, int n_sweeps) {
+    if (!valid_prec(prec) || n_i < 0 || grid <= 0 || n_sweeps <= 0) return 0;
+    return slot_layout(prec, n_i, grid).slot_bytes * static_cast<size_t>(n_sweeps);
+}
+
+int nb_sweep(int prec, int kernel_id, int mode, const void* packed, long n_j, int jt_begin, int jt_end,
+             int jt2_begin, int jt2_end, long i_begin, long n_i, double eps2, void* workspace,
+             size_t workspace_bytes, int slot, int grid, void* stream) {
+    if (!valid_prec(prec) || !valid_kid(kernel_id) || !valid_mode(mode)) return NB_E_INVALID_ARG;
+    if (!packed || !workspace || n_j < 0 || n_i < 0 || i_begin < 0 || grid <= 0 || slot < 0 || slot >= 4)
+        return NB_E_INVALID_ARG;
+    if (jt_end < jt_begin || jt2_end < jt2_begin || jt_begin < 0 || jt2_begin < 0) return NB_E_INVALID_ARG;
+    const long long n_pad = nb_padded_count(n_j);
+    const int n_tiles = static_cast<int>(n_pad / TJ);
+    if (jt_end > n_tiles || jt2_end > n_tiles) return NB_E_INVALID_ARG;
+    const SlotLayout L = slot_layout(prec, n_i, grid);
+    if (workspace_bytes < L.slot_bytes * static_cast<size_t>(slot + 1)) return NB_E_WORKSPACE;
+    if (n_i == 0) return 0;
+
+    const int IB = block_i_for(prec, kernel_id);
+    SweepArgs a;
+    a.packed = static_cast<const unsigned char*>(packed);
+    a.n_j = n_j;
+    a.n_pad = n_pad;
+    a.jtA0 = jt_begin;
+    a.lenA = jt_end - jt_begin;
+    a.jtB0 = jt2_begin;
+    a.lenB = jt2_end - jt2_begin;
+    a.n_jt = a.lenA + a.lenB;
+    a.n_ib = static_cast<int>((n_i + IB - 1) / IB);
+    a.i_begin = i_begin;
+    a.n_i = n_i;
+    a.total = static_cast<long long>(a.n_ib) * a.n_jt;
+    a.eps2 = eps2;
+    unsigned char* base = static_cast<unsigned char*>(workspace) + L.slot_bytes * static_cast<size_t>(slot);
+    a.full = base;
+    a.part = base + L.part_off;
+    if (a.n_jt == 0) return 0;   // nothing to sweep; nb_finish skips slots with n_jt == 0
+    return dispatch(prec, kernel_id, mode, OP_LAUNCH, &a, grid, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+/* kernel_id is needed because the i-block size of a slot depends on the tuning variant in force for it */
+int nb_finish(int prec, int kernel_id, int mode, long n_i, int grid, int n_sweeps, const int* n_jt,
+              const void* workspace, double G, void* acc, void* phi, void* stream) {
+    if (!valid_prec(prec) || !valid_kid(kernel_id) || !valid_mode(mode) || n_i < 0 || grid <= 0 || n_sweeps < 1 ||
+        n_sweeps > 4 || !n_jt || !workspace)
+        return NB_E_INVALID_ARG;
+    if (!(mode & NB_MODE_FORCE)) acc = nullptr;
+    if (!(mode & NB_MODE_POT)) phi = nullptr;
+    const SlotLayout L = slot_layout(prec, n_i, grid);
+    return nb_launch_finish(prec, n_i, grid, block_i_for(prec, kernel_id), n_sweeps, n_jt, workspace, L.slot_bytes,
+                            L.part_off, G, acc, phi, static_cast<cudaStream_t>(stream));
+}
+
+int nb_direct(int prec, int kernel_id, int mode, const void* pos, int pos_dt, const void* mass, int mass_dt,
+              double mass_scalar, const void* h, int h_dt, double h_scalar, long n, double G, double eps2,
+              void* packed, void* workspace, size_t workspace_bytes, int grid, void* acc, void* phi,
+              void* stream) {
+    if (n < 0) return NB_E_INVALID_ARG;
+    if (n == 0) return 0;
+    const long n_pad = nb_padded_count(n);
+    int rc = nb_pack(prec, kernel_id, packed, 0, pos, pos_dt, mass, mass_dt, mass_scalar, h, h_dt, h_scalar, n,
+                     n_pad, eps2, stream);
+    if (rc) return rc;
+    const int n_tiles = static_cast<int>(n_pad / TJ);
+    rc = nb_sweep(prec, kernel_id, mode, packed, n, 0, n_tiles, 0, 0, 0, n, eps2, workspace, workspace_bytes, 0,
+                  grid, stream);
+    if (rc) return rc;
+    return nb_finish(prec, kernel_id, mode, n, grid, 1, &n_tiles, workspace, G, acc, phi, stream);
+}
+
+int nb_kick_drift_pack(int prec, double* pos, double* vel, const void* acc, int acc_dt, const double* acc_ext,
+                       void* packed, long first, long n, double dt_half, double dt, void* stream) {
+    if (!valid_prec(prec) || !pos || !vel || !acc || n < 0 || first < 0) return NB_E_INVALID_ARG;
+    return nb_launch_kick_drift_pack(prec, pos, vel, acc, acc_dt, acc_ext, packed, first, n, dt_half, dt,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int nb_kick(double* vel, const void* acc, int acc_dt, const double* acc_ext, long n, double dt_half,
+            void* stream) {
+    if (!vel || !acc || n < 0) return NB_E_INVALID_ARG;
+    return nb_launch_kick(vel, acc, acc_dt, acc_ext, n, dt_half, static_cast<cudaStream_t>(stream));
+}
+
+size_t nb_energy_workspace_bytes(long n) { return nb_energy_ws_bytes(n); }
+
+int nb_energy(const double* vel, const void* mass, int mass_dt, const void* phi, int phi_dt, const void* acc,
+              int acc_dt, long n, double* partials, double* out, void* stream) {
+    if (!vel || !mass || !partials || !out || n < 0) return NB_E_INVALID_ARG;
+    return nb_launch_energy(vel, mass, mass_dt, phi, phi_dt, acc, acc_dt, n, partials, out,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int nb_ubench(int which, int iters, double* lane_ops_per_s, double* ms) {
+    return nb_ubench_impl(which, iters, lane_ops_per_s, ms);
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+// nb_common.cuh — shared constants, PTX helpers and the softened pair kernels.
+//
+// Hand-written for sm_100a (B200).  No tensor cores on purpose: the r^-3 pair
+// sum is not a dense contraction; the bound is the FP32 / FP64 CUDA-core pipe.
+//
+// Reference maths restated here (never copied): the five softening kernels of
+//   nbody_streams/cuda_kernels.py:22-87   (force, float)   / :687-752  (double)
+//   nbody_streams/cuda_kernels.py:373-436 (potential)      / :1228-1297 (double)
+// and the max-softening pair rule of cuda_kernels.py:150.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/nbody_sm100.h"
+
+namespace nb {
+
+constexpr int TJ      = 256;   // particles per j-tile (one bulk async copy)
+constexpr int THREADS = 128;   // threads per sweep CTA
+constexpr int STAGES  = 3;     // shared-memory ring depth for j-tiles
+
+constexpr int I_F32 = 8;       // i-particles per thread, f32 (4 packed f32x2 pairs)
+constexpr int I_F64 = 4;       // i-particles per thread, f64
+constexpr int IB_F32 = THREADS * I_F32;   // i-particles per work unit
+constexpr int IB_F64 = THREADS * I_F64;
+
+// One tile of the packed buffer is structure-of-arrays: [x TJ][y TJ][z TJ][m TJ][c TJ].
+// SoA lets the inner loop fetch 4 (f32) / 2 (f64) j-particles per LDS.128 and lets the
+// i-pairs be fetched as aligned 64-bit (x_i, x_i+1) register pairs for FADD2/FFMA2.
+constexpr int TILE_BYTES_F32 = TJ * 20;
+constexpr int TILE_BYTES_F64 = TJ * 40;
+constexpr int COMP_X = 0, COMP_Y = 1, COMP_Z = 2, COMP_M = 3, COMP_C = 4;
+
+// ---------------------------------------------------------------------------
+// PTX: mbarrier + 1-D bulk async copy (TMA engine; SASS UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "NB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra NB_DONE;\n"
+        "bra NB_WAIT;\n"
+        "NB_DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.RSQ
+    return y;
+}
+// Full-precision double rsqrt: MUFU.RSQ64H seed (~2^-21) + one third-order
+// (Halley-type) correction: error ~ (5/16) e^3 < 2^-60.
+__device__ __forceinline__ double rsqrt_f64(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double xy = x * y;
+    const double e  = fma(-xy, y, 1.0);
+    const double t  = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, t, y);
+}
+
+// ---------------------------------------------------------------------------
+// Packed FP32x2 (Blackwell FADD2 / FMUL2 / FFMA2).  A pair lives in ONE 64-bit
+// register (type f2) so ptxas keeps it in an aligned register pair for its whole
+// life; going through float2 + the __f*2_rn intrinsics makes ptxas rebuild
+// loop-invariant pairs with MOVs on every use (measured in SASS).
+// ---------------------------------------------------------------------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 splat(float v) { return pk(v, v); }   // becomes a .F32 broadcast operand
+__device__ __forceinline__ void upk(f2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ float lo_of(f2 v) { float a, b; upk(v, a, b); return a; }
+__device__ __forceinline__ float hi_of(f2 v) { float a, b; upk(v, a, b); return b; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// Cubic-spline (Monaghan 1992) pieces, evaluated only for pairs with r < h.
+// Restates cuda_kernels.py:61-87 (force) and :405-436 (potential); T = float
+// or double.  Returns the 1/r^3-equivalent factor w and the -1/r-equivalent phi.
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T spline_w_inside(T r, T h) {
+    const T hinv  = T(1) / h;
+    const T q     = r * hinv;
+    const T h3inv = hinv * hinv * hinv;
+    if (q < T(1e-8)) return h3inv * T(10.666666666666666);
+    const T q2 = q * q;
+    if (q <= T(0.5)) return h3inv * (T(10.666666666666666) + q2 * (T(32.0) * q - T(38.4)));
+    const T q3 = q2 * q;
+    return h3inv * (T(21.333333333333333) + q * (T(-48.0) + q * (T(38.4) - T(10.666666666666667) * q)) -
+                    T(0.06666666666666667) / q3);
+}
+template <typename T>
+__device__ __forceinline__ T spline_phi_inside(T r, T h) {
+    const T hinv = T(1) / h;
+    const T q    = r * hinv;
+    if (q < T(1e-8)) return T(-2.8) * hinv;
+    const T q2 = q * q;
+    if (q <= T(0.5)) {
+        const T q4 = q2 * q2;
+        return (T(-2.8) + q2 * (T(5.333333333333333) + q4 * (T(6.4) * q - T(9.6)))) * hinv;
+    }
+    return (T(-3.2) + T(0.06666666666666667) / q +
+            q2 * (T(10.666666666666666) + q * (T(-16.0) + q * (T(9.6) - T(2.1333333333333333) * q)))) *
+           hinv;
+}
+
+// integer helpers for the stream-K split: CTA c owns units [unit_begin(c), unit_begin(c+1))
+__host__ __device__ __forceinline__ long long unit_begin(long long total, int c, int grid) {
+    return (total * (long long)c) / (long long)grid;
+}
+
+}  // namespace nb

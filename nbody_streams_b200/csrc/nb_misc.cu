@@ -1,0 +1,316 @@
+// nb_misc.cu — O(N) kernels around the sweep: pack, finish (stream-K fix-up),
+// fused KDK kick/drift/pack, energy reductions.
+//
+// Reference behaviour replaced (all were separate CuPy array expressions, one
+// launch each): fields.py:596-598,601-614 (column split, scalar broadcast),
+// fields.py:832-836 (float4 pack), fields.py:855-858 ((N,3) assembly),
+// run.py:188,195 (dtype casts), run.py:672,675,695 (kick / drift),
+// run.py:619-623 (energies).
+#include "nb_sweep.cuh"
+
+namespace nb {
+
+// ---------------------------------------------------------------------------
+// pack
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double load_as_double(const void* p, int dt, long long idx) {
+    return dt == NB_DT_F64 ? static_cast<const double*>(p)[idx] : static_cast<double>(static_cast<const float*>(p)[idx]);
+}
+
+template <typename T>
+__global__ void pack_kernel(T* __restrict__ tiles, const void* __restrict__ pos, int pos_dt,
+                            const void* __restrict__ mass, int mass_dt, double mass_scalar,
+                            const void* __restrict__ h, int h_dt, double h_scalar, long long n, long long n_pad,
+                            double eps2, int add_eps) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= n_pad) return;
+    const long long t = idx / TJ;
+    const int k       = static_cast<int>(idx - t * TJ);
+    T* tb = tiles + t * (TJ * 5);
+    T x = T(0), y = T(0), z = T(0), m = T(0), c = T(1);
+    if (idx < n) {
+        // cast to the kernel dtype FIRST (reference: pos.astype(dtype), run.py:188), then square h
+        x = static_cast<T>(load_as_double(pos, pos_dt, 3 * idx + 0));
+        y = static_cast<T>(load_as_double(pos, pos_dt, 3 * idx + 1));
+        z = static_cast<T>(load_as_double(pos, pos_dt, 3 * idx + 2));
+        m = static_cast<T>(mass ? load_as_double(mass, mass_dt, idx) : mass_scalar);
+        const T hh = static_cast<T>(h ? load_as_double(h, h_dt, idx) : h_scalar);
+        c = hh * hh;
+        if (add_eps) c += static_cast<T>(eps2);
+    }
+    tb[COMP_X * TJ + k] = x;
+    tb[COMP_Y * TJ + k] = y;
+    tb[COMP_Z * TJ + k] = z;
+    tb[COMP_M * TJ + k] = m;
+    tb[COMP_C * TJ + k] = c;
+}
+
+// ---------------------------------------------------------------------------
+// finish: add the stream-K pieces of every sweep slot in fixed order
+// ---------------------------------------------------------------------------
+struct FinishArgs {
+    const unsigned char* ws;     // workspace base
+    size_t slot_bytes;           // bytes per sweep slot
+    size_t part_off;             // offset of part[] inside a slot
+    int n_sweeps;
+    int n_jt[4];
+    int grid;
+    int IB;
+    int n_ib;
+    long long n_i;
+    double G;
+};
+
+template <typename PT /*float4|double4*/, typename OT /*float|double*/>
+__global__ void finish_kernel(const FinishArgs a, OT* __restrict__ acc, OT* __restrict__ phi) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= a.n_i) return;
+    const int ib = static_cast<int>(i / a.IB);
+    const int li = static_cast<int>(i - static_cast<long long>(ib) * a.IB);
+    double sx = 0.0, sy = 0.0, sz = 0.0, sp = 0.0;
+    for (int s = 0; s < a.n_sweeps; ++s) {
+        const int n_jt = a.n_jt[s];
+        if (n_jt <= 0) continue;
+        const unsigned char* slot = a.ws + static_cast<size_t>(s) * a.slot_bytes;
+        const PT* full = reinterpret_cast<const PT*>(slot);
+        const PT* part = reinterpret_cast<const PT*>(slot + a.part_off);
+        const long long total = static_cast<long long>(a.n_ib) * n_jt;
+        const long long ub = static_cast<long long>(ib) * n_jt, ue = ub + n_jt;
+        // first CTA whose unit range contains ub
+        int c = static_cast<int>((ub * a.grid) / total);
+        if (c >= a.grid) c = a.grid - 1;
+        while (c > 0 && unit_begin(total, c, a.grid) > ub) --c;
+        while (c + 1 < a.grid && unit_begin(total, c + 1, a.grid) <= ub) ++c;
+        for (; c < a.grid; ++c) {
+            const long long cb = unit_begin(total, c, a.grid), ce = unit_begin(total, c + 1, a.grid);
+            if (cb >= ue) break;
+            const long long sb = cb > ub ? cb : ub, se = ce < ue ? ce : ue;
+            if (se <= sb) continue;   // CTA with an empty range
+            PT v;
+            if (sb == ub && se == ue) v = full[static_cast<size_t>(ib) * a.IB + li];
+            else v = part[(static_cast<size_t>(c) * 2 + (sb == cb ? 0 : 1)) * a.IB + li];
+            sx += static_cast<double>(v.x);
+            sy += static_cast<double>(v.y);
+            sz += static_cast<double>(v.z);
+            sp += static_cast<double>(v.w);
+        }
+    }
+    if (acc) {
+        acc[3 * i + 0] = static_cast<OT>(a.G * sx);
+        acc[3 * i + 1] = static_cast<OT>(a.G * sy);
+        acc[3 * i + 2] = static_cast<OT>(a.G * sz);
+    }
+    if (phi) phi[i] = static_cast<OT>(-a.G * sp);
+}
+
+// ---------------------------------------------------------------------------
+// KDK pieces
+// ---------------------------------------------------------------------------
+template <typename AT /*acc dtype*/, typename T /*packed dtype*/>
+__global__ void kick_drift_pack_kernel(double* __restrict__ pos, double* __restrict__ vel,
+                                       const AT* __restrict__ acc, const double* __restrict__ acc_ext,
+                                       T* __restrict__ tiles, long long first, long long n, double dt_half,
+                                       double dt) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double a = static_cast<double>(acc[3 * i + d]);
+        if (acc_ext) a += acc_ext[3 * i + d];
+        // same operation order as the reference: vel += acc*(dt/2); pos += vel*dt  (run.py:672,675)
+        const double v = vel[3 * i + d] + a * dt_half;
+        vel[3 * i + d] = v;
+        p[d] = pos[3 * i + d] + v * dt;
+        pos[3 * i + d] = p[d];
+    }
+    if (tiles) {
+        const long long g = first + i;
+        const long long t = g / TJ;
+        const int k       = static_cast<int>(g - t * TJ);
+        T* tb = tiles + t * (TJ * 5);
+        tb[COMP_X * TJ + k] = static_cast<T>(p[0]);
+        tb[COMP_Y * TJ + k] = static_cast<T>(p[1]);
+        tb[COMP_Z * TJ + k] = static_cast<T>(p[2]);
+    }
+}
+
+template <typename AT>
+__global__ void kick_kernel(double* __restrict__ vel, const AT* __restrict__ acc,
+                            const double* __restrict__ acc_ext, long long n3, double dt_half) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n3) return;
+    double a = static_cast<double>(acc[e]);
+    if (acc_ext) a += acc_ext[e];
+    vel[e] += a * dt_half;
+}
+
+// ---------------------------------------------------------------------------
+// energy / momentum reduction (deterministic two-stage)
+// ---------------------------------------------------------------------------
+constexpr int ERED_THREADS = 256;
+constexpr int ERED_PER_BLOCK = 4096;
+
+__global__ void energy_stage1(const double* __restrict__ vel, const void* __restrict__ mass, int mass_dt,
+                              const void* __restrict__ phi, int phi_dt, const void* __restrict__ acc, int acc_dt,
+                              long long n, double* __restrict__ partials) {
+    __shared__ double sh[8][ERED_THREADS / 32];
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long base = static_cast<long long>(blockIdx.x) * ERED_PER_BLOCK;
+    for (int o = threadIdx.x; o < ERED_PER_BLOCK; o += ERED_THREADS) {
+        const long long i = base + o;
+        if (i >= n) break;
+        const double m  = load_as_double(mass, mass_dt, i);
+        const double vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+        v[0] += 0.5 * m * (vx * vx + vy * vy + vz * vz);
+        if (phi) v[1] += 0.5 * m * load_as_double(phi, phi_dt, i);
+        v[2] += m * vx;
+        v[3] += m * vy;
+        v[4] += m * vz;
+        if (acc) {
+            v[5] += m * load_as_double(acc, acc_dt, 3 * i);
+            v[6] += m * load_as_double(acc, acc_dt, 3 * i + 1);
+            v[7] += m * load_as_double(acc, acc_dt, 3 * i + 2);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], off);
+        if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double s = 0.0;
+        for (int w = 0; w < ERED_THREADS / 32; ++w) s += sh[threadIdx.x][w];
+        partials[static_cast<size_t>(blockIdx.x) * 8 + threadIdx.x] = s;
+    }
+}
+
+__global__ void energy_stage2(const double* __restrict__ partials, int n_blocks, double* __restrict__ out) {
+    // 8 warps, one per quantity; each warp adds its column in fixed order
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int b = lane; b < n_blocks; b += 32) s += partials[static_cast<size_t>(b) * 8 + q];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if (lane == 0) out[q] = s;
+}
+
+}  // namespace nb
+
+// ===========================================================================
+// host-side launchers (called from nb_capi.cu)
+// ===========================================================================
+using namespace nb;
+
+#define NB_CUDA_OK(expr)                    \
+    do {                                    \
+        cudaError_t e_ = (expr);            \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+int nb_launch_pack(int prec, int kernel_id, void* packed, long long first, const void* pos, int pos_dt,
+                   const void* mass, int mass_dt, double mass_scalar, const void* h, int h_dt, double h_scalar,
+                   long long n, long long n_pad, double eps2, cudaStream_t st) {
+    if (n_pad <= 0) return 0;
+    const int add_eps = (kernel_id == NB_KERNEL_PLUMMER || kernel_id == NB_KERNEL_DEHNEN_K1 ||
+                         kernel_id == NB_KERNEL_DEHNEN_K2);
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((n_pad + threads - 1) / threads);
+    const long long t0 = first / TJ;
+    if (prec == NB_PREC_F64) {
+        double* tiles = static_cast<double*>(packed) + t0 * (TJ * 5);
+        pack_kernel<double><<<blocks, threads, 0, st>>>(tiles, pos, pos_dt, mass, mass_dt, mass_scalar, h, h_dt,
+                                                        h_scalar, n, n_pad, eps2, add_eps);
+    } else {
+        float* tiles = static_cast<float*>(packed) + t0 * (TJ * 5);
+        pack_kernel<float><<<blocks, threads, 0, st>>>(tiles, pos, pos_dt, mass, mass_dt, mass_scalar, h, h_dt,
+                                                       h_scalar, n, n_pad, eps2, add_eps);
+    }
+    NB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int nb_launch_finish(int prec, long long n_i, int grid, int IB, int n_sweeps, const int* n_jt, const void* ws,
+                     size_t slot_bytes, size_t part_off, double G, void* acc, void* phi, cudaStream_t st) {
+    if (n_i <= 0) return 0;
+    FinishArgs a;
+    a.ws = static_cast<const unsigned char*>(ws);
+    a.slot_bytes = slot_bytes;
+    a.part_off = part_off;
+    a.n_sweeps = n_sweeps;
+    for (int s = 0; s < 4; ++s) a.n_jt[s] = s < n_sweeps ? n_jt[s] : 0;
+    a.grid = grid;
+    a.IB = IB;
+    a.n_ib = static_cast<int>((n_i + IB - 1) / IB);
+    a.n_i = n_i;
+    a.G = G;
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((n_i + threads - 1) / threads);
+    if (prec == NB_PREC_F32)
+        finish_kernel<float4, float><<<blocks, threads, 0, st>>>(a, static_cast<float*>(acc), static_cast<float*>(phi));
+    else if (prec == NB_PREC_F64)
+        finish_kernel<double4, double><<<blocks, threads, 0, st>>>(a, static_cast<double*>(acc),
+                                                                   static_cast<double*>(phi));
+    else
+        finish_kernel<double4, float><<<blocks, threads, 0, st>>>(a, static_cast<float*>(acc), static_cast<float*>(phi));
+    NB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int nb_launch_kick_drift_pack(int prec, double* pos, double* vel, const void* acc, int acc_dt,
+                              const double* acc_ext, void* packed, long long first, long long n, double dt_half,
+                              double dt, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((n + threads - 1) / threads);
+    if (prec == NB_PREC_F64) {
+        double* tiles = static_cast<double*>(packed);
+        if (acc_dt == NB_DT_F64)
+            kick_drift_pack_kernel<double, double><<<blocks, threads, 0, st>>>(
+                pos, vel, static_cast<const double*>(acc), acc_ext, tiles, first, n, dt_half, dt);
+        else
+            kick_drift_pack_kernel<float, double><<<blocks, threads, 0, st>>>(
+                pos, vel, static_cast<const float*>(acc), acc_ext, tiles, first, n, dt_half, dt);
+    } else {
+        float* tiles = static_cast<float*>(packed);
+        if (acc_dt == NB_DT_F64)
+            kick_drift_pack_kernel<double, float><<<blocks, threads, 0, st>>>(
+                pos, vel, static_cast<const double*>(acc), acc_ext, tiles, first, n, dt_half, dt);
+        else
+            kick_drift_pack_kernel<float, float><<<blocks, threads, 0, st>>>(
+                pos, vel, static_cast<const float*>(acc), acc_ext, tiles, first, n, dt_half, dt);
+    }
+    NB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int nb_launch_kick(double* vel, const void* acc, int acc_dt, const double* acc_ext, long long n, double dt_half,
+                   cudaStream_t st) {
+    if (n <= 0) return 0;
+    const long long n3 = 3 * n;
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((n3 + threads - 1) / threads);
+    if (acc_dt == NB_DT_F64)
+        kick_kernel<double><<<blocks, threads, 0, st>>>(vel, static_cast<const double*>(acc), acc_ext, n3, dt_half);
+    else
+        kick_kernel<float><<<blocks, threads, 0, st>>>(vel, static_cast<const float*>(acc), acc_ext, n3, dt_half);
+    NB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+size_t nb_energy_ws_bytes(long long n) {
+    const long long blocks = (n + ERED_PER_BLOCK - 1) / ERED_PER_BLOCK;
+    return static_cast<size_t>(blocks > 0 ? blocks : 1) * 8 * sizeof(double);
+}
+
+int nb_launch_energy(const double* vel, const void* mass, int mass_dt, const void* phi, int phi_dt,
+                     const void* acc, int acc_dt, long long n, double* partials, double* out, cudaStream_t st) {
+    const int blocks = static_cast<int>((n + ERED_PER_BLOCK - 1) / ERED_PER_BLOCK);
+    if (blocks > 0)
+        energy_stage1<<<blocks, ERED_THREADS, 0, st>>>(vel, mass, mass_dt, phi, phi_dt, acc, acc_dt, n, partials);
+    energy_stage2<<<1, 256, 0, st>>>(partials, blocks, out);
+    NB_CUDA_OK(cudaGetLastError());
+    return 0;
+}

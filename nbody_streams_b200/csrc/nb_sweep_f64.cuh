@@ -1,0 +1,203 @@
+// nb_sweep_f64.cuh — the FP64 pair sweep (NB_PREC_F64).
+//
+// Replaces nbody_forces_kernel<double> / nbody_potential_kernel<double>
+// (reference nbody_streams/cuda_kernels.py:755-864, :1299-1387).
+//
+// Same persistent stream-K / TMA-ring structure as the f32 sweep; the pair
+// arithmetic is scalar DFMA with NI i-particles register-blocked per thread and
+// a hand-rolled full-precision rsqrt (MUFU.RSQ64H seed + one third-order step,
+// 5 FP64 ops) instead of the library's longer sequence.  Bound: FP64 pipe.
+#pragma once
+#include "nb_sweep.cuh"
+
+namespace nb {
+
+template <int KID, int MODE, bool MASK>
+__device__ __forceinline__ void pair_f64(const double xj, const double yj, const double zj, double mj,
+                                         const double cj, const double xi, const double yi, const double zi,
+                                         const double ci, double& ax, double& ay, double& az, double& sp,
+                                         const double eps2, const bool valid) {
+    const double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    double c, h2;
+    if (KID == NB_KERNEL_NEWTONIAN) {
+        c = h2 = eps2;
+    } else if (KID == NB_KERNEL_SPLINE) {
+        c  = eps2;
+        h2 = fmax(cj, ci);
+    } else {
+        c = h2 = fmax(cj, ci);
+    }
+    if (MASK && !valid) {
+        mj = 0.0;
+        c  = 1.0;
+    }
+    double d = fma(dx, dx, fma(dy, dy, fma(dz, dz, c)));
+    bool inside = false;
+    if (KID == NB_KERNEL_SPLINE) {
+        inside = (d < h2) && (!MASK || valid);
+        d = fmax(d, h2);
+    }
+    const double rinv = rsqrt_f64(d);
+    const double mr   = mj * rinv;
+    if (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2) {
+        const double rinv2 = rinv * rinv;
+        const double t     = h2 * rinv2;
+        if (MODE & NB_MODE_POT) {
+            const double pf = (KID == NB_KERNEL_DEHNEN_K1) ? fma(0.5, t, 1.0) : fma(t, fma(0.375, t, 0.5), 1.0);
+            sp = fma(mr, pf, sp);
+        }
+        if (MODE & NB_MODE_FORCE) {
+            const double ff = (KID == NB_KERNEL_DEHNEN_K1) ? fma(1.5, t, 1.0) : fma(t, fma(3.75, t, 1.5), 1.0);
+            const double f  = (mr * rinv2) * ff;
+            ax = fma(f, dx, ax);
+            ay = fma(f, dy, ay);
+            az = fma(f, dz, az);
+        }
+    } else {
+        double f = 0.0;
+        if (MODE & NB_MODE_FORCE) f = mr * (rinv * rinv);
+        double p = mr;
+        if (KID == NB_KERNEL_SPLINE) {
+            if (inside) {   // exact Monaghan spline instead of the clamped Newtonian value
+                const double dr = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+                const double r = sqrt(dr), h = sqrt(h2);
+                if (MODE & NB_MODE_FORCE) f = mj * spline_w_inside<double>(r, h);
+                if (MODE & NB_MODE_POT) p = -mj * spline_phi_inside<double>(r, h);
+            }
+        }
+        if (MODE & NB_MODE_POT) sp += p;
+        if (MODE & NB_MODE_FORCE) {
+            ax = fma(f, dx, ax);
+            ay = fma(f, dy, ay);
+            az = fma(f, dz, az);
+        }
+    }
+}
+
+template <int NI>
+struct IState64 {
+    double x[NI], y[NI], z[NI], c[NI];
+    double ax[NI], ay[NI], az[NI], sp[NI];
+};
+
+template <int KID, int MODE, bool MASK, int NI>
+__device__ __forceinline__ void tile_f64(const unsigned char* __restrict__ stage, IState64<NI>& S,
+                                         const double eps2, const long long jg0, const long long ig0,
+                                         const long long n_j) {
+    const double* __restrict__ sX = reinterpret_cast<const double*>(stage) + COMP_X * TJ;
+    const double* __restrict__ sY = reinterpret_cast<const double*>(stage) + COMP_Y * TJ;
+    const double* __restrict__ sZ = reinterpret_cast<const double*>(stage) + COMP_Z * TJ;
+    const double* __restrict__ sM = reinterpret_cast<const double*>(stage) + COMP_M * TJ;
+    const double* __restrict__ sC = reinterpret_cast<const double*>(stage) + COMP_C * TJ;
+#pragma unroll 1
+    for (int j0 = 0; j0 < TJ; j0 += 2) {
+        const double2 x2 = *reinterpret_cast<const double2*>(sX + j0);
+        const double2 y2 = *reinterpret_cast<const double2*>(sY + j0);
+        const double2 z2 = *reinterpret_cast<const double2*>(sZ + j0);
+        const double2 m2 = *reinterpret_cast<const double2*>(sM + j0);
+        double2 c2 = make_double2(0.0, 0.0);
+        if (KID != NB_KERNEL_NEWTONIAN) c2 = *reinterpret_cast<const double2*>(sC + j0);
+#pragma unroll
+        for (int q = 0; q < NI; ++q) {
+            bool v0 = true, v1 = true;
+            if (MASK) {
+                const long long ig = ig0 + static_cast<long long>(THREADS) * q;
+                const long long jg = jg0 + j0;
+                v0 = (jg < n_j) && (jg != ig);
+                v1 = (jg + 1 < n_j) && (jg + 1 != ig);
+            }
+            pair_f64<KID, MODE, MASK>(x2.x, y2.x, z2.x, m2.x, c2.x, S.x[q], S.y[q], S.z[q], S.c[q], S.ax[q], S.ay[q],
+                                      S.az[q], S.sp[q], eps2, v0);
+            pair_f64<KID, MODE, MASK>(x2.y, y2.y, z2.y, m2.y, c2.y, S.x[q], S.y[q], S.z[q], S.c[q], S.ax[q], S.ay[q],
+                                      S.az[q], S.sp[q], eps2, v1);
+        }
+    }
+}
+
+template <int KID, int MODE, int NI, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int IB = THREADS * NI;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * TILE_BYTES_F64);
+
+    const int tid = threadIdx.x;
+    const int cta = blockIdx.x, grid = gridDim.x;
+    const long long u0 = unit_begin(a.total, cta, grid);
+    const long long u1 = unit_begin(a.total, cta + 1, grid);
+    const int n_units  = static_cast<int>(u1 - u0);
+    const double eps2  = a.eps2;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int k) {
+        const long long u = u0 + k;
+        const int jl      = static_cast<int>(u % a.n_jt);
+        const int gt      = local_to_global_tile(a, jl);
+        uint64_t* bar     = &full_bar[k % STAGES];
+        mbar_expect_tx(bar, TILE_BYTES_F64);
+        bulk_g2s(smem + (k % STAGES) * TILE_BYTES_F64, a.packed + static_cast<size_t>(gt) * TILE_BYTES_F64,
+                 TILE_BYTES_F64, bar);
+    };
+    if (tid == 0) {
+        for (int k = 0; k < STAGES - 1 && k < n_units; ++k) issue(k);
+    }
+
+    long long u = u0;
+    int k = 0;
+    while (u < u1) {
+        const int ib  = static_cast<int>(u / a.n_jt);
+        const int jl0 = static_cast<int>(u - static_cast<long long>(ib) * a.n_jt);
+        const long long rem = u1 - u;
+        const int jl1 = static_cast<int>(min(static_cast<long long>(a.n_jt), jl0 + rem));
+
+        const long long ig_block = a.i_begin + static_cast<long long>(ib) * IB;
+        const long long ig0      = ig_block + tid;
+        IState64<NI> S;
+#pragma unroll
+        for (int q = 0; q < NI; ++q) {
+            const long long ig = ig0 + static_cast<long long>(THREADS) * q;
+            S.x[q] = S.y[q] = S.z[q] = 0.0;
+            S.c[q] = 1.0;
+            if (ig < a.n_pad) {
+                const long long t = ig / TJ;
+                const int kk      = static_cast<int>(ig - t * TJ);
+                const double* tb  = reinterpret_cast<const double*>(a.packed + static_cast<size_t>(t) * TILE_BYTES_F64);
+                S.x[q] = tb[COMP_X * TJ + kk];
+                S.y[q] = tb[COMP_Y * TJ + kk];
+                S.z[q] = tb[COMP_Z * TJ + kk];
+                S.c[q] = tb[COMP_C * TJ + kk];
+            }
+            S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0.0;
+        }
+
+        for (int jl = jl0; jl < jl1; ++jl, ++k) {
+            __syncthreads();
+            if (tid == 0 && k + STAGES - 1 < n_units) issue(k + STAGES - 1);
+            mbar_wait(&full_bar[k % STAGES], (k / STAGES) & 1);
+
+            const int gt        = local_to_global_tile(a, jl);
+            const long long jg0 = static_cast<long long>(gt) * TJ;
+            const bool masked   = (jg0 + TJ > a.n_j) || (jg0 < ig_block + IB && jg0 + TJ > ig_block);
+            const unsigned char* stage = smem + (k % STAGES) * TILE_BYTES_F64;
+            if (masked)
+                tile_f64<KID, MODE, true, NI>(stage, S, eps2, jg0, ig0, a.n_j);
+            else
+                tile_f64<KID, MODE, false, NI>(stage, S, eps2, jg0, ig0, a.n_j);
+        }
+
+        const bool is_full = (jl0 == 0 && jl1 == a.n_jt);
+        const size_t base  = is_full ? static_cast<size_t>(ib) * IB
+                                     : (static_cast<size_t>(cta) * 2 + (u == u0 ? 0 : 1)) * IB;
+        double4* dst = reinterpret_cast<double4*>(is_full ? a.full : a.part) + base;
+#pragma unroll
+        for (int q = 0; q < NI; ++q) dst[tid + THREADS * q] = make_double4(S.ax[q], S.ay[q], S.az[q], S.sp[q]);
+        u += jl1 - jl0;
+    }
+}
+
+}  // namespace nb

@@ -1,0 +1,3 @@
+// softening kernel id 1 (plummer = roofline headline, spline = API default): all tuning variants
+#include "nb_dispatch.cuh"
+NB_DEFINE_KID(1, true)

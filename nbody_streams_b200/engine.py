@@ -1,0 +1,343 @@
+"""Device-resident direct-summation engine: sharded state + the per-step launch sequence.
+
+New layer (the reference is single-GPU only).  One process
+per GPU; ``torch.distributed`` (NCCL over NVLink) is the plumbing.  i-particles
+are sharded contiguously and tile-aligned across ranks; every rank keeps the
+whole packed j-buffer (20 B/particle f32, 40 B f64).  Per step:
+
+    kick+drift+repack own shard (1 fused kernel)
+      -> all-gather of the packed shards on a side stream, in place
+      -> overlap mode : sweep own j-tiles now, the remote tiles once the gather lands
+         deterministic: one sweep over all tiles in global order after the gather
+      -> finish (fixed-order fix-up, x G)
+      -> half kick
+
+With world size 1 the same code runs without any collective, which is the path
+``run_nbody_gpu`` uses on a single GPU.
+
+Host-side pieces that do not need a GPU (``ShardLayout``, ``allgather_shards``,
+``gather_rows``) are plain functions so the N>1 logic is testable with the
+``gloo`` backend on CPU tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import DT_F32, DT_F64, MODE_BOTH, MODE_FORCE, MODE_POT, PREC_F64
+
+TILE_J = 256  # must equal nb_tile_j(); asserted when the library is loaded
+
+
+# ---------------------------------------------------------------------------
+# shard layout (pure Python)
+# ---------------------------------------------------------------------------
+@dataclass(frozen=True)
+class ShardLayout:
+    """Contiguous, tile-aligned split of N particles over `world` ranks.
+
+    Every rank owns `tiles_per_rank` tiles = `shard` particle slots; only the
+    tail of the global range is padding, so a particle's slot index equals its
+    original index."""
+
+    N: int
+    world: int
+    tile: int = TILE_J
+
+    @property
+    def tiles_total(self) -> int:
+        return (self.N + self.tile - 1) // self.tile
+
+    @property
+    def tiles_per_rank(self) -> int:
+        return max(1, (self.tiles_total + self.world - 1) // self.world)
+
+    @property
+    def shard(self) -> int:
+        return self.tiles_per_rank * self.tile
+
+    @property
+    def n_slots(self) -> int:
+        return self.shard * self.world
+
+    def first(self, rank: int) -> int:
+        return rank * self.shard
+
+    def count(self, rank: int) -> int:
+        return int(min(max(self.N - self.first(rank), 0), self.shard))
+
+    def tile_range(self, rank: int) -> tuple[int, int]:
+        return rank * self.tiles_per_rank, (rank + 1) * self.tiles_per_rank
+
+    def rows(self, rank: int) -> slice:
+        f = self.first(rank)
+        return slice(f, f + self.count(rank))
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def group_info(group=None) -> tuple[int, int]:
+    """(rank, world) of the given process group; (0, 1) when torch.distributed is not initialised."""
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def allgather_shards(buf, layout: ShardLayout, rank: int, bytes_per_slot: int, group=None):
+    """In-place all-gather of the equal-size shards of a flat uint8 buffer
+    (shard r occupies bytes [r*S, (r+1)*S), S = layout.shard * bytes_per_slot)."""
+    if layout.world == 1:
+        return None
+    S = layout.shard * bytes_per_slot
+    out = buf[: S * layout.world]
+    inp = buf[rank * S:(rank + 1) * S]
+    return _dist().all_gather_into_tensor(out, inp, group=group)
+
+
+def gather_rows(local, layout: ShardLayout, rank: int, group=None):
+    """All ranks receive the (N, k) concatenation of every rank's real rows."""
+    import torch
+
+    if layout.world == 1:
+        return local
+    k = local.shape[1] if local.dim() > 1 else 1
+    padded = torch.zeros((layout.shard, k), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local.reshape(local.shape[0], k)
+    out = torch.empty((layout.n_slots, k), dtype=local.dtype, device=local.device)
+    _dist().all_gather_into_tensor(out, padded, group=group)
+    out = out[: layout.N]
+    return out if local.dim() > 1 else out.reshape(-1)
+
+
+# ---------------------------------------------------------------------------
+# the engine
+# ---------------------------------------------------------------------------
+class DirectEngine:
+    """Sharded device state and kernels for repeated force evaluations / KDK steps.
+
+    Parameters
+    ----------
+    N : total particle count.
+    mass, softening : scalar or (N,) host arrays (all particles).
+    prec : library precision code; kernel_id : 0..4; G, eps2 : floats.
+    device : torch CUDA device of this rank.
+    group : torch.distributed process group (None = default group / single process).
+    overlap : sweep the local j-shard while the all-gather is in flight (default);
+              False sweeps all tiles in global order after the gather (bitwise equal
+              to the 1-GPU summation order).
+    """
+
+    def __init__(self, N, mass, softening, prec, kernel_id, G, eps2, device, group=None, overlap=True):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.lib = _lib.load()
+        assert self.lib.nb_tile_j() == TILE_J
+        self.N, self.prec, self.kernel_id = int(N), int(prec), int(kernel_id)
+        self.G, self.eps2 = float(G), float(eps2)
+        self.device = torch.device(device)
+        self.group = group
+        self.rank, self.world = group_info(group)
+        self.overlap = bool(overlap) and self.world > 1
+        self.layout = ShardLayout(self.N, self.world)
+        self.first = self.layout.first(self.rank)
+        self.n_local = self.layout.count(self.rank)
+        self.bps = 40 if prec == PREC_F64 else 20
+        self.dtype = torch.float64 if prec == PREC_F64 else torch.float32
+        self.acc_dt = DT_F64 if prec == PREC_F64 else DT_F32
+
+        with torch.cuda.device(self.device):
+            self.packed = torch.zeros(self.layout.n_slots * self.bps, dtype=torch.uint8, device=self.device)
+            self._grids = {}
+            self._ws = None
+            self._ws_bytes = 0
+            self.pos = torch.zeros((self.n_local, 3), dtype=torch.float64, device=self.device)
+            self.vel = torch.zeros((self.n_local, 3), dtype=torch.float64, device=self.device)
+            self.acc = torch.zeros((self.n_local, 3), dtype=self.dtype, device=self.device)
+            self.phi = torch.zeros((self.n_local,), dtype=self.dtype, device=self.device)
+            self._e_part = torch.zeros(self.lib.nb_energy_workspace_bytes(max(self.n_local, 1)) // 8,
+                                       dtype=torch.float64, device=self.device)
+            self._e_out = torch.zeros(8, dtype=torch.float64, device=self.device)
+            self.comm_stream = torch.cuda.Stream(self.device) if self.world > 1 else None
+
+        # static per-particle data (host -> device once); masses in the KERNEL dtype semantics
+        self._mass_host = None if np.isscalar(mass) else np.ascontiguousarray(mass)
+        self._mass_scalar = float(mass) if np.isscalar(mass) else 0.0
+        self._h_host = None if np.isscalar(softening) else np.ascontiguousarray(softening)
+        self._h_scalar = float(softening) if np.isscalar(softening) else 0.0
+        self.mass_local = self._local_mass_tensor()
+        self.launches = 0   # kernels launched by this engine (bench.py gpu_launches)
+
+    # -- helpers ------------------------------------------------------------
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _local_mass_tensor(self):
+        torch = self.torch
+        if self._mass_host is None:
+            return torch.full((max(self.n_local, 1),), self._mass_scalar, dtype=torch.float64, device=self.device)[: self.n_local]
+        m = np.asarray(self._mass_host[self.layout.rows(self.rank)], dtype=np.float64)
+        return torch.from_numpy(np.ascontiguousarray(m)).to(self.device)
+
+    def _grid(self, mode):
+        g = self._grids.get(mode)
+        if g is None:
+            out = C.c_int(0)
+            with self.torch.cuda.device(self.device):
+                _lib.check(self.lib.nb_sweep_grid(self.prec, self.kernel_id, mode, C.byref(out)))
+            g = self._grids[mode] = int(out.value)
+        return g
+
+    def _workspace(self, grid):
+        need = self.lib.nb_workspace_bytes(self.prec, max(self.n_local, 1), grid, 2)
+        if self._ws is None or self._ws_bytes < need:
+            self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+            self._ws_bytes = need
+        return self._ws
+
+    # -- state --------------------------------------------------------------
+    def load_state(self, phase_space: np.ndarray) -> None:
+        """Upload this rank's rows of the (N,6) float64 state and pack ALL particles
+        (every rank has the full initial positions, so no collective is needed here)."""
+        torch = self.torch
+        xv = np.asarray(phase_space, dtype=np.float64)
+        rows = self.layout.rows(self.rank)
+        with torch.cuda.device(self.device):
+            self.pos.copy_(torch.from_numpy(np.ascontiguousarray(xv[rows, :3])))
+            self.vel.copy_(torch.from_numpy(np.ascontiguousarray(xv[rows, 3:6])))
+            pos_all = torch.from_numpy(np.ascontiguousarray(xv[:, :3])).to(self.device)
+            self.pack_all(pos_all)
+
+    def pack_all(self, pos_all) -> None:
+        """(Re)build every packed record from a device (N,3) position array."""
+        torch = self.torch
+        dt_mass = self.torch.float64
+        mass_t = h_t = None
+        if self._mass_host is not None:
+            mass_t = torch.from_numpy(np.asarray(self._mass_host)).to(self.device)
+            if mass_t.dtype not in (torch.float32, torch.float64):
+                mass_t = mass_t.to(dt_mass)
+        if self._h_host is not None:
+            h_t = torch.from_numpy(np.asarray(self._h_host)).to(self.device)
+            if h_t.dtype not in (torch.float32, torch.float64):
+                h_t = h_t.to(dt_mass)
+        code = lambda t: DT_F64 if t.dtype == torch.float64 else DT_F32  # noqa: E731
+        pos_all = pos_all.contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nb_pack(
+                self.prec, self.kernel_id, self.packed.data_ptr(), 0,
+                pos_all.data_ptr(), code(pos_all),
+                mass_t.data_ptr() if mass_t is not None else None, code(mass_t) if mass_t is not None else 0,
+                self._mass_scalar,
+                h_t.data_ptr() if h_t is not None else None, code(h_t) if h_t is not None else 0,
+                self._h_scalar,
+                self.N, self.layout.n_slots, self.eps2, self._stream()))
+            self.launches += 1
+            # keep operand tensors alive until the kernel has consumed them
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def state_numpy(self) -> np.ndarray:
+        """(N,6) float64 on the host, identical on all ranks."""
+        torch = self.torch
+        xv_local = torch.cat([self.pos, self.vel], dim=1)
+        full = gather_rows(xv_local, self.layout, self.rank, self.group)
+        return full.cpu().numpy()
+
+    # -- force evaluation -----------------------------------------------------
+    def compute(self, mode: int = MODE_FORCE, positions_changed: bool = True) -> None:
+        """Sweep + finish into self.acc / self.phi for this rank's i-particles.
+        Assumes the packed records of this rank's shard are current; all-gathers them
+        first when world > 1 and `positions_changed`."""
+        torch, lib = self.torch, self.lib
+        grid = self._grid(mode)
+        ws = self._workspace(grid)
+        t0, t1 = self.layout.tile_range(self.rank)
+        n_tiles = self.layout.tiles_per_rank * self.world
+        n_jt = (C.c_int * 4)(0, 0, 0, 0)
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            if self.world > 1 and positions_changed:
+                self.comm_stream.wait_stream(cur)          # shard records are written on `cur`
+                with torch.cuda.stream(self.comm_stream):
+                    allgather_shards(self.packed, self.layout, self.rank, self.bps, self.group)
+            if self.n_local > 0:
+                if self.overlap:
+                    # slot 0: own shard (no dependency on the collective)
+                    _lib.check(lib.nb_sweep(self.prec, self.kernel_id, mode, self.packed.data_ptr(), self.N,
+                                            t0, t1, 0, 0, self.first, self.n_local, self.eps2,
+                                            ws.data_ptr(), self._ws_bytes, 0, grid, self._stream()))
+                    n_jt[0] = t1 - t0
+                    cur.wait_stream(self.comm_stream)
+                    # slot 1: every other rank's tiles, as two ranges around mine
+                    _lib.check(lib.nb_sweep(self.prec, self.kernel_id, mode, self.packed.data_ptr(), self.N,
+                                            0, t0, t1, n_tiles, self.first, self.n_local, self.eps2,
+                                            ws.data_ptr(), self._ws_bytes, 1, grid, self._stream()))
+                    n_jt[1] = n_tiles - (t1 - t0)
+                    n_sweeps = 2
+                    self.launches += 2
+                else:
+                    if self.world > 1:
+                        cur.wait_stream(self.comm_stream)
+                    _lib.check(lib.nb_sweep(self.prec, self.kernel_id, mode, self.packed.data_ptr(), self.N,
+                                            0, n_tiles, 0, 0, self.first, self.n_local, self.eps2,
+                                            ws.data_ptr(), self._ws_bytes, 0, grid, self._stream()))
+                    n_jt[0] = n_tiles
+                    n_sweeps = 1
+                    self.launches += 1
+                _lib.check(lib.nb_finish(self.prec, self.kernel_id, mode, self.n_local, grid, n_sweeps, n_jt,
+                                         ws.data_ptr(), self.G,
+                                         self.acc.data_ptr() if mode & MODE_FORCE else None,
+                                         self.phi.data_ptr() if mode & MODE_POT else None, self._stream()))
+                self.launches += 1
+            elif self.world > 1:
+                cur.wait_stream(self.comm_stream)
+
+    # -- KDK pieces -----------------------------------------------------------
+    def kick_drift(self, dt: float, acc_ext=None) -> None:
+        """vel += acc*dt/2 ; pos += vel*dt ; refresh own packed x,y,z (one fused kernel)."""
+        if self.n_local == 0:
+            return
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.nb_kick_drift_pack(
+                self.prec, self.pos.data_ptr(), self.vel.data_ptr(), self.acc.data_ptr(), self.acc_dt,
+                acc_ext.data_ptr() if acc_ext is not None else None,
+                self.packed.data_ptr(), self.first, self.n_local, 0.5 * dt, dt, self._stream()))
+        self.launches += 1
+
+    def kick(self, dt: float, acc_ext=None) -> None:
+        """vel += acc*dt/2."""
+        if self.n_local == 0:
+            return
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.nb_kick(self.vel.data_ptr(), self.acc.data_ptr(), self.acc_dt,
+                                        acc_ext.data_ptr() if acc_ext is not None else None,
+                                        self.n_local, 0.5 * dt, self._stream()))
+        self.launches += 1
+
+    def energy(self, with_phi: bool = True, with_acc: bool = False) -> np.ndarray:
+        """[KE, PE, px, py, pz, fx, fy, fz] summed over all ranks (float64, host)."""
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            if self.n_local > 0:
+                _lib.check(self.lib.nb_energy(
+                    self.vel.data_ptr(), self.mass_local.data_ptr(), DT_F64,
+                    self.phi.data_ptr() if with_phi else None, self.acc_dt,
+                    self.acc.data_ptr() if with_acc else None, self.acc_dt,
+                    self.n_local, self._e_part.data_ptr(), self._e_out.data_ptr(), self._stream()))
+                self.launches += 2
+            else:
+                self._e_out.zero_()
+            out = self._e_out.clone()
+            if self.world > 1:
+                _dist().all_reduce(out, group=self.group)
+        return out.cpu().numpy()
+
+
+__all__ = ["ShardLayout", "DirectEngine", "allgather_shards", "gather_rows", "group_info", "TILE_J"]

@@ -1,0 +1,442 @@
+"""GPU force / potential dispatch — drop-in for the GPU half of the reference's
+``nbody_streams/fields.py``.
+
+Same public names, argument order, defaults, return dtypes and error types as
+the reference:
+
+* ``compute_nbody_forces_gpu``    (reference fields.py:664-864)
+* ``compute_nbody_potential_gpu`` (reference fields.py:866-1018)
+* ``get_gpu_info``                (reference fields.py:1149-1185)
+* ``G_DEFAULT``, ``KERNEL_MAP``   (reference fields.py:90-100)
+
+What changes underneath: instead of CuPy-JIT-compiled kernel strings
+(reference fields.py:417-483) the calls go through ctypes into the compiled
+sm_100a library ``libnbody_sm100.so``; device arrays are torch CUDA tensors
+(no CuPy in this stack).  ``return_cupy=True`` returns a :class:`DeviceArray`
+(a ``torch.Tensor`` subclass with the ``.get()`` / ``.astype()`` /
+``__cuda_array_interface__`` surface reference callers use).
+
+There is no CPU fallback in this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Literal
+
+import numpy as np
+
+from . import _lib
+from ._lib import DT_F32, DT_F64, MODE_BOTH, MODE_FORCE, MODE_POT, PREC_F32, PREC_F32_COMP, PREC_F64
+
+# Default gravitational constant (kpc, km/s, Msun) — reference fields.py:90
+G_DEFAULT = 4.300917270069976e-06
+
+KERNEL_TYPES = Literal["newtonian", "plummer", "dehnen_k1", "dehnen_k2", "spline"]
+
+# reference fields.py:94-100
+KERNEL_MAP = {
+    "newtonian": 0,
+    "plummer": 1,
+    "dehnen_k1": 2,
+    "dehnen_k2": 3,
+    "spline": 4,
+}
+
+# precision string -> (library precision code, numpy dtype); reference fields.py:104-115
+_PRECISION_MAP = {
+    "float64": (PREC_F64, np.float64),
+    "float32": (PREC_F32, np.float32),
+    "float32_kahan": (PREC_F32_COMP, np.float32),
+}
+
+# Regularisation added to r^2.  The reference GPU path adds 1e-15 (fields.py:825),
+# its CPU path adds (1e-15)^2 = 1e-30 (fields.py:237,1083-1086).  float64 follows the
+# CPU convention (needed for 1e-12 agreement with the Numba path), float32 the GPU one.
+EPS2_DEFAULT = {"float64": 1e-30, "float32": 1e-15, "float32_kahan": 1e-15}
+
+
+def _torch():
+    return _lib.require_cuda()
+
+
+class DeviceArray:  # replaced below by a torch.Tensor subclass once torch is importable
+    pass
+
+
+def _make_device_array_type():
+    import torch
+
+    class DeviceArray(torch.Tensor):
+        """torch CUDA tensor with the small CuPy-like surface reference callers rely on
+        (``.get()`` -> NumPy, reference _chandrasekhar.py:48-54 and run.py:204;
+        ``.astype``; ``__cuda_array_interface__`` comes from torch.Tensor)."""
+
+        def get(self) -> np.ndarray:
+            return self.detach().as_subclass(torch.Tensor).cpu().numpy()
+
+        def astype(self, dtype, copy: bool = True):
+            tdt = _np_to_torch_dtype(np.dtype(dtype))
+            out = self.to(tdt)
+            if copy and out.data_ptr() == self.data_ptr():
+                out = out.clone()
+            return out.as_subclass(DeviceArray)
+
+        def __array__(self, dtype=None, copy=None):
+            a = self.get()
+            return a.astype(dtype) if dtype is not None else a
+
+    return DeviceArray
+
+
+try:  # torch is part of the stack; keep module importable for the CPU-only unit tests
+    DeviceArray = _make_device_array_type()  # type: ignore[misc]
+except Exception:  # pragma: no cover
+    pass
+
+
+def _np_to_torch_dtype(dt: np.dtype):
+    import torch
+
+    return {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dt)]
+
+
+def _is_device_array(x) -> bool:
+    """True for torch CUDA tensors and anything exposing __cuda_array_interface__ (CuPy...)."""
+    try:
+        import torch
+
+        if isinstance(x, torch.Tensor):
+            return x.is_cuda
+    except ImportError:  # pragma: no cover
+        pass
+    return hasattr(x, "__cuda_array_interface__")
+
+
+def _as_cuda_tensor(x, device):
+    import torch
+
+    if isinstance(x, torch.Tensor):
+        return x.as_subclass(torch.Tensor)
+    return torch.as_tensor(x, device=device)  # consumes __cuda_array_interface__ zero-copy
+
+
+# ---------------------------------------------------------------------------
+# validation (host side; identical checks / messages to reference fields.py:485-565)
+# ---------------------------------------------------------------------------
+def _validate_inputs(pos, mass, softening, precision, kernel):
+    prec_key = precision.lower()
+    if prec_key not in _PRECISION_MAP:
+        raise ValueError(f"Precision must be one of {list(_PRECISION_MAP.keys())}")
+    dtype_np = _PRECISION_MAP[prec_key][1]
+
+    if _is_device_array(pos):
+        if pos.ndim != 2 or pos.shape[1] != 3:
+            raise ValueError(f"pos must have shape (N, 3), got {tuple(pos.shape)}")
+        N = pos.shape[0]
+        pos_cpu = None
+    else:
+        pos_cpu = np.asarray(pos, dtype=dtype_np)
+        if pos_cpu.ndim != 2 or pos_cpu.shape[1] != 3:
+            raise ValueError(f"pos must have shape (N, 3), got {pos_cpu.shape}")
+        N = pos_cpu.shape[0]
+
+    def _one(val, label):
+        if np.isscalar(val):
+            return None, float(val)
+        if _is_device_array(val):
+            if val.shape[0] != N:
+                raise ValueError(f"{label} must have length N={N}, got {val.shape[0]}")
+            return None, None
+        arr = np.asarray(val, dtype=dtype_np)
+        if arr.ndim == 0:
+            return None, float(arr)
+        if arr.shape[0] != N:
+            raise ValueError(f"{label} must have length N={N}, got {arr.shape[0]}")
+        return arr, None
+
+    mass_cpu, mass_scalar = _one(mass, "mass")
+    h_cpu, h_scalar = _one(softening, "softening")
+
+    if kernel.lower() not in KERNEL_MAP:
+        raise ValueError(f"Invalid kernel '{kernel}'. Must be one of: {list(KERNEL_MAP.keys())}")
+
+    return {
+        "N": N,
+        "pos_cpu": pos_cpu,
+        "mass_cpu": mass_cpu,
+        "mass_scalar": mass_scalar,
+        "h_cpu": h_cpu,
+        "h_scalar": h_scalar,
+        "kernel_id": KERNEL_MAP[kernel.lower()],
+        "dtype_np": dtype_np,
+        "prec": _PRECISION_MAP[prec_key][0],
+        "original_pos": pos,
+        "original_mass": mass,
+        "original_h": softening,
+    }
+
+
+# ---------------------------------------------------------------------------
+# device-side plumbing
+# ---------------------------------------------------------------------------
+_GRID_CACHE: dict = {}
+_SCRATCH: dict = {}
+
+
+def _grid_for(prec: int, kernel_id: int, mode: int, device) -> int:
+    lib = _lib.load()
+    key = (device.index, prec, kernel_id, mode, lib.nb_get_variant(prec))
+    g = _GRID_CACHE.get(key)
+    if g is None:
+        out = C.c_int(0)
+        _lib.check(lib.nb_sweep_grid(prec, kernel_id, mode, C.byref(out)))
+        g = _GRID_CACHE[key] = int(out.value)
+    return g
+
+
+def _scratch(device, tag: str, nbytes: int):
+    """Grow-only per-device scratch (packed particle records, stream-K workspace).
+
+    Like the reference's module-level kernel cache (fields.py:396) this is not
+    thread-safe; kernels using it are ordered by the CUDA stream they run on."""
+    import torch
+
+    key = (device.index, tag)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _SCRATCH[key] = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    return buf
+
+
+def _dt_code(t) -> int:
+    import torch
+
+    if t.dtype == torch.float64:
+        return DT_F64
+    if t.dtype == torch.float32:
+        return DT_F32
+    raise ValueError(f"unsupported dtype {t.dtype}")
+
+
+def _device_operand(arr_cpu, scalar, original, dtype_t, device):
+    """-> (tensor or None, scalar): host array -> H2D, device array -> as is, scalar -> broadcast in the pack kernel."""
+    import torch
+
+    if scalar is not None:
+        return None, float(scalar)
+    if arr_cpu is not None:
+        return torch.from_numpy(np.ascontiguousarray(arr_cpu)).to(device), 0.0
+    t = _as_cuda_tensor(original, device)
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(dtype_t)
+    return t.contiguous(), 0.0
+
+
+def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, mode, G, eps2, dtype_np):
+    """pack + sweep + finish on the current stream.  Returns (acc|None, phi|None) torch tensors."""
+    import torch
+
+    lib = _lib.load()
+    device = pos_t.device
+    dtype_t = _np_to_torch_dtype(dtype_np)
+    acc = torch.empty((N, 3), dtype=dtype_t, device=device) if mode & MODE_FORCE else None
+    phi = torch.empty((N,), dtype=dtype_t, device=device) if mode & MODE_POT else None
+    if N == 0:
+        return acc, phi
+    with torch.cuda.device(device):
+        grid = _grid_for(prec, kernel_id, mode, device)
+        packed = _scratch(device, "packed", lib.nb_packed_bytes(prec, N))
+        ws_bytes = lib.nb_workspace_bytes(prec, N, grid, 1)
+        ws = _scratch(device, "workspace", ws_bytes)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(
+            lib.nb_direct(
+                prec, kernel_id, mode,
+                pos_t.data_ptr(), _dt_code(pos_t),
+                mass_t.data_ptr() if mass_t is not None else None, _dt_code(mass_t) if mass_t is not None else 0,
+                float(mass_scalar),
+                h_t.data_ptr() if h_t is not None else None, _dt_code(h_t) if h_t is not None else 0,
+                float(h_scalar),
+                N, float(G), float(eps2),
+                packed.data_ptr(), ws.data_ptr(), ws_bytes, grid,
+                acc.data_ptr() if acc is not None else None,
+                phi.data_ptr() if phi is not None else None,
+                stream,
+            )
+        )
+    return acc, phi
+
+
+def _prepare(pos, mass, softening, precision, kernel, skip_validation, device):
+    """Common front end of the two public calls -> device operands."""
+    import torch
+
+    if skip_validation:
+        # Hot-loop path (reference fields.py:790-799): trust device arrays of the right dtype.
+        prec_key = precision.lower()
+        prec, dtype_np = _PRECISION_MAP[prec_key]
+        kernel_id = KERNEL_MAP[kernel.lower()]
+        dev = device or (pos.device if hasattr(pos, "device") and isinstance(pos, torch.Tensor) else torch.device("cuda", torch.cuda.current_device()))
+        pos_t = _as_cuda_tensor(pos, dev).contiguous()
+        N = pos_t.shape[0]
+        mass_t, mass_s = (None, float(mass)) if np.isscalar(mass) else (_as_cuda_tensor(mass, dev).contiguous(), 0.0)
+        h_t, h_s = (None, float(softening)) if np.isscalar(softening) else (_as_cuda_tensor(softening, dev).contiguous(), 0.0)
+        return pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np
+
+    v = _validate_inputs(pos, mass, softening, precision, kernel)
+    dtype_np = v["dtype_np"]
+    dtype_t = _np_to_torch_dtype(dtype_np)
+    if device is None:
+        if v["pos_cpu"] is None and isinstance(pos, torch.Tensor):
+            device = pos.device
+        else:
+            device = torch.device("cuda", torch.cuda.current_device())
+    if v["pos_cpu"] is None:
+        pos_t = _as_cuda_tensor(v["original_pos"], device)
+        if pos_t.dtype not in (torch.float32, torch.float64):
+            pos_t = pos_t.to(dtype_t)
+        pos_t = pos_t.contiguous()
+    else:
+        pos_t = torch.from_numpy(np.ascontiguousarray(v["pos_cpu"])).to(device)
+    mass_t, mass_s = _device_operand(v["mass_cpu"], v["mass_scalar"], v["original_mass"], dtype_t, device)
+    h_t, h_s = _device_operand(v["h_cpu"], v["h_scalar"], v["original_h"], dtype_t, device)
+    return pos_t, mass_t, mass_s, h_t, h_s, v["N"], v["prec"], v["kernel_id"], dtype_np
+
+
+# ---------------------------------------------------------------------------
+# PUBLIC API
+# ---------------------------------------------------------------------------
+def compute_nbody_forces_gpu(
+    pos,
+    mass,
+    softening=0.0,
+    G: float = G_DEFAULT,
+    precision: Literal["float32", "float64", "float32_kahan"] = "float32_kahan",
+    kernel: KERNEL_TYPES = "spline",
+    return_cupy: bool = False,
+    skip_validation: bool = False,
+    *,
+    eps2: float | None = None,
+    device=None,
+):
+    """Direct-summation gravitational accelerations on the GPU.
+
+    Drop-in for reference ``compute_nbody_forces_gpu`` (fields.py:664-864):
+    ``a_i = G sum_{j != i} m_j K(r_ij^2 + eps2, max(h_i, h_j)) (r_j - r_i)``.
+
+    Parameters are those of the reference.  ``pos`` (N,3), ``mass`` scalar or
+    (N,), ``softening`` scalar or (N,) may be NumPy arrays, torch tensors (CPU
+    or CUDA) or any object exposing ``__cuda_array_interface__``.  Returns an
+    (N,3) array of the kernel dtype (float32 for 'float32'/'float32_kahan',
+    float64 for 'float64'): NumPy by default, a device array when
+    ``return_cupy=True``.
+
+    Keyword-only extensions (defaults reproduce the reference call): ``eps2``
+    overrides the r^2 regularisation (see ``EPS2_DEFAULT``), ``device`` picks
+    the CUDA device.
+
+    Raises ImportError without a CUDA device / built library, ValueError for
+    bad shapes, precision or kernel names, RuntimeError for CUDA failures.
+    """
+    _torch()
+    ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
+    pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
+    e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
+    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np)
+    if return_cupy:
+        return acc.as_subclass(DeviceArray)
+    return acc.cpu().numpy()
+
+
+def compute_nbody_potential_gpu(
+    pos,
+    mass,
+    softening=0.0,
+    G: float = G_DEFAULT,
+    precision: Literal["float32", "float64", "float32_kahan"] = "float32_kahan",
+    kernel: KERNEL_TYPES = "spline",
+    return_cupy: bool = False,
+    skip_validation: bool = False,
+    *,
+    eps2: float | None = None,
+    device=None,
+):
+    """Gravitational potential at each particle, ``phi_i = G sum_{j != i} m_j Phi(r_ij)``.
+
+    Drop-in for reference ``compute_nbody_potential_gpu`` (fields.py:866-1018);
+    returns (N,) in the kernel dtype.  ``dehnen_k2`` follows the reference GPU
+    formula (cuda_kernels.py:394-402), which differs from the reference CPU one
+    (fields.py:280-288) — see DESIGN.md.
+    """
+    _torch()
+    ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
+    pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
+    e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
+    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np)
+    if return_cupy:
+        return phi.as_subclass(DeviceArray)
+    return phi.cpu().numpy()
+
+
+def compute_nbody_forces_potential_gpu(
+    pos,
+    mass,
+    softening=0.0,
+    G: float = G_DEFAULT,
+    precision: Literal["float32", "float64", "float32_kahan"] = "float32_kahan",
+    kernel: KERNEL_TYPES = "spline",
+    return_cupy: bool = False,
+    skip_validation: bool = False,
+    *,
+    eps2: float | None = None,
+    device=None,
+):
+    """Accelerations AND potential from one fused sweep (new; the reference needs two
+    O(N^2) passes, run.py:611-634).  Returns ``(acc (N,3), phi (N,))``."""
+    _torch()
+    ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
+    pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
+    e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
+    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np)
+    if return_cupy:
+        return acc.as_subclass(DeviceArray), phi.as_subclass(DeviceArray)
+    return acc.cpu().numpy(), phi.cpu().numpy()
+
+
+def get_gpu_info() -> dict:
+    """Same keys as reference ``get_gpu_info`` (fields.py:1149-1185)."""
+    try:
+        torch = _torch()
+    except ImportError:
+        return {"available": False}
+    try:
+        lib = _lib.load()
+        sm, maj, mnr, clk = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        tot, free = C.c_size_t(), C.c_size_t()
+        name = C.create_string_buffer(256)
+        with torch.cuda.device(torch.cuda.current_device()):
+            torch.cuda.init()
+            _lib.check(lib.nb_device_info(C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(tot), C.byref(free),
+                                          C.byref(clk), name, 256))
+        return {
+            "available": True,
+            "device_name": name.value.decode("utf-8"),
+            "compute_capability": f"{maj.value}{mnr.value}",
+            "memory_total": int(tot.value),
+            "memory_free": int(free.value),
+            "sm_count": int(sm.value),
+        }
+    except Exception as e:  # noqa: BLE001 - mirror the reference: report, don't raise
+        print(e)
+        return {"available": False, "error": str(e)}
+
+
+__all__ = [
+    "compute_nbody_forces_gpu",
+    "compute_nbody_potential_gpu",
+    "compute_nbody_forces_potential_gpu",
+    "get_gpu_info",
+    "G_DEFAULT",
+    "KERNEL_MAP",
+    "DeviceArray",
+]

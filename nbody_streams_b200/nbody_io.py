@@ -1,0 +1,155 @@
+"""Snapshot / restart files in the reference's on-disk formats.
+
+Only the writer side the integrator loop needs; schemas
+follow reference nbody_streams/nbody_io.py so that its ``ParticleReader`` and
+``continue_run`` keep working on files written here:
+
+* ``restart.npz``  — keys ``phase_space, time, step, snapshot_counter`` and, for
+  multi-species runs, ``mass_arr, softening_arr, species_names, species_N``
+  (reference nbody_io.py:930-986, loader :989-1035);
+* ``snapshot.h5`` / ``snapshot.NNN.h5`` — group ``snapshots/snap.###`` (gzip
+  float64 (N,6)) with ``snap_time.###`` attributes, and ``properties/<species>/
+  {N, m | m_array, eps | eps_array}``, ``properties/time_step``
+  (reference nbody_io.py:770-928).  Needs h5py, imported lazily;
+* ``snapshot.times`` — text table "snap_index time" (reference nbody_io.py:1037-1074).
+"""
+from __future__ import annotations
+
+import math
+from pathlib import Path
+
+import numpy as np
+
+
+def _per_particle(value, n):
+    if np.isscalar(value):
+        return np.full(n, float(value), dtype=np.float64)
+    return np.asarray(value, dtype=np.float64)
+
+
+def _snapshot_filename(output_dir: Path, snap_index: int, single_file, num_files_to_write,
+                       total_expected_snapshots) -> Path:
+    if single_file is None:
+        single_file = num_files_to_write is None
+    n_files = int(num_files_to_write) if (num_files_to_write is not None and num_files_to_write > 0) else 1
+    if single_file or n_files == 1:
+        return output_dir / "snapshot.h5"
+    if total_expected_snapshots is not None and total_expected_snapshots > 0:
+        per_file = math.ceil(total_expected_snapshots / n_files)
+        idx = min(int(snap_index) // per_file, n_files - 1)
+    else:
+        idx = int(snap_index) % n_files
+    return output_dir / f"snapshot.{idx:03d}.h5"
+
+
+def _save_snapshot(phase_space, snap_index, time, output_dir, *, species=None, num_dark=None, num_star=None,
+                   mass_dark=None, mass_star=None, time_step=None, eps_dark=None, eps_star=None,
+                   single_file=None, num_files_to_write=None, total_expected_snapshots=None) -> None:
+    """Append ``snap.<index>`` to the HDF5 snapshot file (never overwrites an existing dataset)."""
+    try:
+        import h5py
+    except ImportError as e:
+        raise ImportError("h5py is required to write snapshots (save_snapshots=True)") from e
+
+    output_dir = Path(output_dir)
+    output_dir.mkdir(parents=True, exist_ok=True)
+    fname = _snapshot_filename(output_dir, snap_index, single_file, num_files_to_write, total_expected_snapshots)
+    with h5py.File(fname, "a") as f:
+        snaps = f.require_group("snapshots")
+        name = f"snap.{snap_index:03d}"
+        if name in snaps:
+            return
+        snaps.create_dataset(name, data=phase_space, compression="gzip")
+        snaps.attrs[f"snap_time.{snap_index:03d}"] = float(time)
+        props = f.require_group("properties")
+        if species is not None:
+            if "n_species" not in props.attrs:
+                props.attrs["n_species"] = len(species)
+                props.attrs["species_names"] = np.array([s.name.encode("utf-8") for s in species])
+            for s in species:
+                if s.name in props:
+                    continue
+                grp = props.create_group(s.name)
+                grp.create_dataset("N", data=int(s.N))
+                for values, scalar_key, array_key in ((_per_particle(s.mass, s.N), "m", "m_array"),
+                                                      (_per_particle(s.softening, s.N), "eps", "eps_array")):
+                    if values.size and np.all(values == values[0]):
+                        grp.create_dataset(scalar_key, data=float(values[0]))
+                    else:
+                        grp.create_dataset(array_key, data=values, compression="gzip")
+        else:
+            n = phase_space.shape[0]
+            if num_dark is None and num_star is None:
+                num_dark, num_star = n, 0
+            elif num_star is None:
+                num_star = n - int(num_dark)
+            for key, cnt, m, eps in (("dark", num_dark, mass_dark, eps_dark), ("star", num_star, mass_star, eps_star)):
+                if key not in props:
+                    grp = props.create_group(key)
+                    grp.create_dataset("N", data=int(cnt))
+                    grp.create_dataset("m", data=float(1.0 if m is None else m))
+                    grp.create_dataset("eps", data=float(0.0 if eps is None else eps))
+        if "time_step" not in props:
+            props.create_dataset("time_step", data=float(0.0 if time_step is None else time_step))
+
+
+def _save_restart(phase_space, time, step, output_dir, snapshot_counter, *, mass_arr=None, softening_arr=None,
+                  species_names=None, species_N=None) -> None:
+    """Write ``restart.npz`` (compressed) for crash recovery / ``continue_run=True``."""
+    out = Path(output_dir)
+    out.mkdir(parents=True, exist_ok=True)
+    payload = {
+        "phase_space": phase_space,
+        "time": np.float64(time),
+        "step": np.int64(step),
+        "snapshot_counter": np.int64(snapshot_counter),
+    }
+    if mass_arr is not None:
+        payload["mass_arr"] = np.asarray(mass_arr, dtype=np.float64)
+    if softening_arr is not None:
+        payload["softening_arr"] = np.asarray(softening_arr, dtype=np.float64)
+    if species_names is not None:
+        payload["species_names"] = np.array([n.encode("utf-8") for n in species_names])
+    if species_N is not None:
+        payload["species_N"] = np.array(species_N, dtype=np.int64)
+    np.savez_compressed(out / "restart.npz", **payload)
+
+
+def _load_restart(output_dir):
+    """-> (phase_space, time, step, snapshot_counter, mass_arr, softening_arr, species_names, species_N) or None."""
+    path = Path(output_dir) / "restart.npz"
+    if not path.exists():
+        return None
+    data = np.load(path, allow_pickle=False)
+    files = set(data.files)
+    names = None
+    if "species_names" in files:
+        names = [n.decode("utf-8") if isinstance(n, (bytes, np.bytes_)) else str(n) for n in data["species_names"]]
+    return (
+        data["phase_space"],
+        float(data["time"]),
+        int(data["step"]),
+        int(data["snapshot_counter"]) if "snapshot_counter" in files else 0,
+        data["mass_arr"] if "mass_arr" in files else None,
+        data["softening_arr"] if "softening_arr" in files else None,
+        names,
+        [int(n) for n in data["species_N"]] if "species_N" in files else None,
+    )
+
+
+def _update_snapshot_times(output_dir, snap_index: int, time: float) -> None:
+    """Insert / update the row for ``snap_index`` in ``snapshot.times`` (sorted, unique indices)."""
+    out = Path(output_dir)
+    out.mkdir(parents=True, exist_ok=True)
+    path = out / "snapshot.times"
+    rows = {}
+    if path.exists():
+        try:
+            arr = np.atleast_2d(np.loadtxt(str(path), comments="#"))
+            if arr.size:
+                rows = {int(r[0]): float(r[1]) for r in arr}
+        except Exception:  # noqa: BLE001 - unreadable file: start over, as the reference does
+            rows = {}
+    rows[int(snap_index)] = float(time)
+    table = np.array(sorted(rows.items()), dtype=float)
+    np.savetxt(str(path), table, fmt="%d %.10e", header="snap_index time", comments="# ")

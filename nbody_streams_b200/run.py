@@ -1,0 +1,424 @@
+"""KDK leapfrog integrator on the B200 engine + Plummer initial conditions.
+
+Drop-in for the GPU half of the reference's ``nbody_streams/run.py``:
+
+* ``run_nbody_gpu``            (reference run.py:327-775)   — same signature, defaults, return
+* ``_compute_accelerations_gpu`` (reference run.py:122-214) — folded into the loop below
+* ``make_plummer_sphere``      (reference run.py:1225-1325) — same seeded output, vectorised
+
+What changes underneath: state (float64 pos/vel) stays on the device in a
+:class:`~nbody_streams_b200.engine.DirectEngine`; a step is 4 kernel launches
+(fused kick+drift+repack, sweep, finish, kick) instead of ~15 CuPy array
+expressions plus a host->device copy of the softening array every step
+(reference run.py:146 note in SURVEY.md 3B).  Launched under ``torchrun`` the
+same function shards the i-particles over all ranks (one process per GPU).
+"""
+from __future__ import annotations
+
+import time as pytime
+from pathlib import Path
+from typing import Callable, Literal
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODE_BOTH, MODE_FORCE, MODE_POT
+from .fields import EPS2_DEFAULT, G_DEFAULT, KERNEL_MAP, _PRECISION_MAP, DeviceArray
+from .nbody_io import _load_restart, _save_restart, _save_snapshot, _update_snapshot_times
+from .species import Species
+
+NBODY_UNITS = {"kpc": 1.0, "Msun": 1.0, "kpc / (km/s)": 1.0, "km/s": 1, "G": G_DEFAULT}
+
+
+# ---------------------------------------------------------------------------
+# initial conditions
+# ---------------------------------------------------------------------------
+def make_plummer_sphere(N: int, M_total: float = 10_000, a: float = 0.01, seed: int = 42069,
+                        G: float = G_DEFAULT) -> tuple[np.ndarray, np.ndarray]:
+    """Plummer sphere in virial equilibrium; returns ((N,6) phase space, (N,) equal masses).
+
+    Produces the same arrays, bit for bit, as the reference generator
+    (run.py:1225-1325) for the same arguments: identical draw order from
+    ``default_rng(seed)`` — radii (inverse CDF), position angles, speeds by
+    Aarseth-Henon-Wielen rejection, velocity angles, centre-of-mass shift.  The
+    reference runs the rejection step as a Python loop of scalar draws (~13 s per
+    million particles); here the (q, g) candidate pairs are drawn in blocks and
+    the generator is then re-positioned exactly behind the last candidate the
+    scalar loop would have consumed, which is ~100x faster and leaves the stream
+    in the same place for the velocity angles.
+    """
+    rng = np.random.default_rng(seed)
+
+    u = rng.uniform(0.0, 1.0, N)
+    r = a / np.sqrt(u ** (-2.0 / 3.0) - 1.0)
+    cos_t = rng.uniform(-1.0, 1.0, N)
+    sin_t = np.sqrt(1.0 - cos_t ** 2)
+    az = rng.uniform(0.0, 2.0 * np.pi, N)
+    x = r * sin_t * np.cos(az)
+    y = r * sin_t * np.sin(az)
+    z = r * cos_t
+
+    v_esc = np.sqrt(2.0 * G * M_total / np.sqrt(r ** 2 + a ** 2))
+
+    # q = v / v_esc distributed as q^2 (1 - q^2)^(7/2); envelope height 0.09375
+    h_max = 0.09375
+    state0 = rng.bit_generator.state
+    accepted = []
+    n_acc = 0
+    n_trials_before = 0          # candidate pairs consumed by completed blocks
+    last_trial = 0               # 1-based index of the candidate that yields the N-th acceptance
+    while n_acc < N:
+        need = N - n_acc
+        block = max(4096, int(need * 5.5) + 1024)       # acceptance rate ~ 0.2
+        d = rng.random(2 * block)
+        qs = d[0::2]                                     # uniform(0, 1)      -> 0 + 1 * d
+        gs = 0.0 + h_max * d[1::2]                       # uniform(0, h_max)  -> 0 + h_max * d
+        ok = np.flatnonzero(gs <= qs ** 2 * (1.0 - qs ** 2) ** 3.5)
+        if ok.size >= need:
+            ok = ok[:need]
+            last_trial = n_trials_before + int(ok[-1]) + 1
+        accepted.append(qs[ok])
+        n_acc += ok.size
+        n_trials_before += block
+    q = np.concatenate(accepted) if accepted else np.empty(0)
+    # put the generator where the scalar loop would have left it: 2 doubles per candidate
+    rng.bit_generator.state = state0
+    rng.bit_generator.advance(2 * last_trial)
+    v_mag = q * v_esc
+
+    cos_tv = rng.uniform(-1.0, 1.0, N)
+    sin_tv = np.sqrt(1.0 - cos_tv ** 2)
+    az_v = rng.uniform(0.0, 2.0 * np.pi, N)
+    vx = v_mag * sin_tv * np.cos(az_v)
+    vy = v_mag * sin_tv * np.sin(az_v)
+    vz = v_mag * cos_tv
+
+    x -= x.mean(); y -= y.mean(); z -= z.mean()
+    vx -= vx.mean(); vy -= vy.mean(); vz -= vz.mean()
+
+    phase_space = np.column_stack([x, y, z, vx, vy, vz])
+    masses = np.full(N, M_total / N, dtype=np.float64)
+    return phase_space, masses
+
+
+# ---------------------------------------------------------------------------
+# external acceleration hooks (reference run.py:197-212, :689-692)
+# ---------------------------------------------------------------------------
+def _external_acc(engine, external_potential, time, full_pos_fn):
+    """(n_local,3) float64 device tensor of the external-potential acceleration."""
+    torch = engine.torch
+    if getattr(external_potential, "accepts_device_arrays", False):
+        # device potential (PotentialGPU-like): evaluate on the device, no host round trip
+        acc_full = external_potential.force(full_pos_fn().as_subclass(DeviceArray), t=time)
+        acc_full = torch.as_tensor(acc_full, device=engine.device).to(torch.float64)
+    else:
+        # host potential (agama.Potential-like): host round trip, as in the reference
+        pos_cpu = full_pos_fn().cpu().numpy()
+        acc_full = torch.from_numpy(np.asarray(external_potential.force(pos_cpu, t=time), dtype=np.float64)).to(
+            engine.device)
+    return acc_full[engine.layout.rows(engine.rank)].contiguous()
+
+
+def run_nbody_gpu(
+    phase_space: np.ndarray,
+    masses: np.ndarray,
+    time_start: float,
+    time_end: float,
+    dt: float,
+    softening,
+    G: float = G_DEFAULT,
+    precision: Literal["float32", "float64", "float32_kahan"] = "float32_kahan",
+    kernel: Literal["newtonian", "plummer", "dehnen_k1", "dehnen_k2", "spline"] = "spline",
+    external_potential=None,
+    external_update_interval: int = 1,
+    force_extra: Callable | None = None,
+    output_dir: str = "./output",
+    save_snapshots: bool = True,
+    snapshots: int = 10,
+    num_files_to_write: int = 1,
+    restart_interval: int = 1000,
+    continue_run: bool = False,
+    overwrite: bool = False,
+    verbose: bool = True,
+    debug_energy: bool = False,
+    species: list[Species] | None = None,
+    *,
+    device=None,
+    group=None,
+    overlap: bool = True,
+    diagnostics: list | None = None,
+    diagnostics_every: int = 0,
+) -> np.ndarray:
+    """GPU direct-summation N-body run with the KDK leapfrog of the reference.
+
+    Positional / keyword arguments, defaults, snapshot schedule, restart files,
+    printed lines and the returned (N,6) float64 array follow reference
+    ``run_nbody_gpu`` (run.py:327-775).  KDK order per step: half kick, drift,
+    ``time += dt``, forces, ``force_extra``, half kick (run.py:672-695).
+
+    Differences (documented in DESIGN.md): masses stay float64 for
+    ``precision='float64'`` (the reference rounds them to float32, run.py:502,
+    which would cap agreement with its own CPU path at ~6e-8); ``debug_energy``
+    takes phi from the same fused sweep as the forces instead of a second
+    O(N^2) pass.
+
+    Keyword-only extensions: ``device`` (CUDA device), ``group``
+    (torch.distributed group; under torchrun the i-particles are sharded over
+    its ranks), ``overlap`` (sweep the local shard while the all-gather is in
+    flight; False = global summation order), ``diagnostics`` (list that
+    receives ``(step, time, KE, PE, px, py, pz)`` every ``diagnostics_every``
+    steps, from the fused sweep).
+    """
+    torch = _lib.require_cuda()   # ImportError when there is no CUDA device / library (reference: "CuPy required")
+
+    phase_space = np.asarray(phase_space, dtype=np.float64)
+    if phase_space.ndim != 2 or phase_space.shape[1] != 6:
+        raise ValueError(f"phase_space must be (N, 6), got {phase_space.shape}")
+    prec_key = precision.lower()
+    if prec_key not in _PRECISION_MAP:
+        raise ValueError(f"Precision must be one of {list(_PRECISION_MAP.keys())}")
+    if kernel.lower() not in KERNEL_MAP:
+        raise ValueError(f"Invalid kernel '{kernel}'. Must be one of: {list(KERNEL_MAP.keys())}")
+    prec, dtype_np = _PRECISION_MAP[prec_key]
+    # reference run.py:502 casts to float32 unconditionally; float64 mode keeps float64 here (see docstring)
+    masses = np.asarray(masses, dtype=np.float64 if prec_key == "float64" else np.float32)
+    N = phase_space.shape[0]
+    if masses.shape[0] != N:
+        raise ValueError(f"masses must have length N={N}, got {masses.shape[0]}")
+    if not np.isscalar(softening):
+        softening = np.asarray(softening, dtype=dtype_np)
+        if softening.shape[0] != N:
+            raise ValueError(f"softening must have length N={N}, got {softening.shape[0]}")
+
+    from .engine import DirectEngine, gather_rows, group_info
+
+    rank, world = group_info(group)
+    is_root = rank == 0
+    verbose = verbose and is_root
+    output_path = Path(output_dir)
+
+    if save_snapshots and not continue_run and is_root:
+        existing = sorted(output_path.glob("snapshot*.h5"))
+        if existing:
+            if overwrite:
+                for f in existing:
+                    f.unlink()
+                if verbose:
+                    print(f"Removed {len(existing)} existing snapshot file(s) in '{output_dir}'.")
+            else:
+                raise FileExistsError(
+                    f"Output directory '{output_dir}' already contains snapshot files: "
+                    f"{[f.name for f in existing]}. "
+                    "Pass overwrite=True to delete them, or continue_run=True to resume."
+                )
+
+    start_step = 0
+    time = time_start
+    snapshot_counter = None
+    xv = phase_space
+    if continue_run:
+        restart_data = _load_restart(output_path)
+        if restart_data is not None:
+            xv, time, start_step, saved_snap_counter = restart_data[:4]
+            snapshot_counter = int(saved_snap_counter)
+            if verbose:
+                print(f"✓ Resuming from step {start_step}, time {time:.6e}")
+
+    _snap_kwargs: dict = dict(num_files_to_write=num_files_to_write, total_expected_snapshots=snapshots)
+    _restart_kwargs: dict = {}
+    if species is not None:
+        _snap_kwargs["species"] = species
+        _snap_kwargs["time_step"] = dt
+        _soft_arr = (np.full(N, float(softening), dtype=np.float64) if np.isscalar(softening)
+                     else np.asarray(softening, dtype=np.float64))
+        _restart_kwargs = dict(mass_arr=masses.astype(np.float64), softening_arr=_soft_arr,
+                               species_names=[s.name for s in species], species_N=[s.N for s in species])
+    else:
+        _snap_kwargs["mass_dark"] = float(masses[0])
+
+    total_steps = int(round((time_end - time_start) / dt))
+    remaining_steps = total_steps - start_step
+    if snapshots > 1:
+        snapshot_steps = np.round(np.linspace(0, total_steps, snapshots)).astype(int)
+    else:
+        snapshot_steps = np.array([total_steps], dtype=int)
+    if snapshot_counter is None:
+        snapshot_counter = int(np.searchsorted(snapshot_steps, start_step, side="left"))
+
+    if verbose:
+        print("=" * 80)
+        print("GPU N-body Integration")
+        print("=" * 80)
+        print(f"Particles: {N:,}")
+        if species is not None:
+            for s in species:
+                print(f"  [{s.name}] N={s.N:,}")
+        print(f"Time: {time_start:.3e} -> {time_end:.3e} (dt={dt:.3e})")
+        print(f"Steps: {total_steps:,} ({remaining_steps:,} remaining)")
+        print(f"Kernel: {kernel}, Softening: {softening if np.isscalar(softening) else 'variable'}")
+        print(f"External potential: {'Yes' if external_potential is not None else 'No'}")
+        if external_potential is not None:
+            print(f"  Update interval: every {external_update_interval} steps")
+        print(f"Snapshots: {snapshots} (every ~{total_steps // max(snapshots, 1):,} steps)")
+        print(f"Restart files: every {restart_interval} steps")
+        if world > 1:
+            print(f"Ranks: {world} (i-particles sharded, overlap={'on' if overlap else 'off'})")
+        print("=" * 80)
+        print("\nTransferring data to GPU...")
+
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    eng = DirectEngine(N, masses, softening, prec, KERNEL_MAP[kernel.lower()], G, EPS2_DEFAULT[prec_key], device,
+                       group=group, overlap=overlap)
+    eng.load_state(xv)
+
+    want_phi = bool(debug_energy or diagnostics is not None)
+    mode = MODE_BOTH if want_phi else MODE_FORCE
+    hooks = external_potential is not None or force_extra is not None
+    cached_ext = None
+
+    def full_pos():
+        return gather_rows(eng.pos, eng.layout, eng.rank, eng.group)
+
+    def full_vel():
+        return gather_rows(eng.vel, eng.layout, eng.rank, eng.group)
+
+    def extra_acc(step, t):
+        """Sum of external-potential (cached) and force_extra accelerations for this rank's rows."""
+        nonlocal cached_ext
+        total = None
+        if external_potential is not None:
+            if step % external_update_interval == 0 or cached_ext is None:
+                cached_ext = _external_acc(eng, external_potential, t, full_pos)
+            total = cached_ext
+        return total
+
+    def add_force_extra(total, t):
+        fe = force_extra(full_pos().as_subclass(DeviceArray), full_vel().as_subclass(DeviceArray), masses, t)
+        fe = torch.as_tensor(np.asarray(fe) if not hasattr(fe, "__cuda_array_interface__") and not isinstance(fe, torch.Tensor) else fe,
+                             device=eng.device).to(torch.float64)[eng.layout.rows(eng.rank)]
+        return fe.contiguous() if total is None else (total + fe).contiguous()
+
+    if verbose:
+        print("Computing initial forces...")
+    eng.compute(mode, positions_changed=False)
+    acc_ext = extra_acc(start_step, time) if hooks else None
+    # the reference applies force_extra only inside the loop (run.py:689-692), not to the initial acceleration
+
+    E_ref = 0.0
+
+    def energies():
+        e = eng.energy(with_phi=True)
+        return float(e[0]), float(e[1]), e
+
+    if want_phi:
+        KE0, PE0, e = energies()
+        E_ref = KE0 + PE0
+        if diagnostics is not None:
+            diagnostics.append((start_step, time, KE0, PE0, float(e[2]), float(e[3]), float(e[4])))
+        if verbose and debug_energy:
+            print(f"  [Energy t=0] KE={KE0:.4e}  PE={PE0:.4e}  E={E_ref:.4e}")
+
+    if verbose:
+        print("\nStarting integration...")
+
+    def host_state():
+        return eng.state_numpy()
+
+    if snapshot_counter < len(snapshot_steps) and snapshot_steps[snapshot_counter] == start_step:
+        if save_snapshots:
+            xv_cpu = host_state()
+            if is_root:
+                _save_snapshot(xv_cpu, snapshot_counter, time, output_path, **_snap_kwargs)
+                _update_snapshot_times(output_path, snapshot_counter, time)
+            if verbose:
+                print(f"Saved snapshot snap: {snapshot_counter:03d} at step {start_step}, time {time:.6e}...")
+        snapshot_counter += 1
+
+    t_start = pytime.perf_counter()
+    _report_every = max(1, remaining_steps // 20)
+
+    for step_i in range(1, remaining_steps + 1):
+        current_step = start_step + step_i
+
+        eng.kick_drift(dt, acc_ext)          # half kick + drift (+ repack own shard), fused
+        time += dt
+        eng.compute(mode)                    # all-gather (world>1) + sweep + finish
+        if hooks:
+            acc_ext = extra_acc(current_step, time)
+            if force_extra is not None:
+                acc_ext = add_force_extra(acc_ext, time)
+        eng.kick(dt, acc_ext)                # half kick
+
+        while snapshot_counter < len(snapshot_steps) and current_step >= snapshot_steps[snapshot_counter]:
+            if save_snapshots:
+                xv_cpu = host_state()
+                if is_root:
+                    _save_snapshot(xv_cpu, snapshot_counter, time, output_path, **_snap_kwargs)
+                    _update_snapshot_times(output_path, snapshot_counter, time)
+                if verbose:
+                    print(f"Saved snapshot id={snapshot_counter:03d} at step {current_step}, time {time:.6e}...",
+                          flush=True)
+            snapshot_counter += 1
+
+        if diagnostics is not None and diagnostics_every and (step_i % diagnostics_every == 0 or
+                                                              step_i == remaining_steps):
+            KE, PE, e = energies()
+            diagnostics.append((current_step, time, KE, PE, float(e[2]), float(e[3]), float(e[4])))
+
+        if (verbose or debug_energy) and step_i % _report_every == 0:
+            line = None
+            if verbose:
+                elapsed = pytime.perf_counter() - t_start
+                rate = step_i / elapsed if elapsed > 0 else 0
+                eta = (remaining_steps - step_i) / rate if rate > 0 else 0
+                line = (f"  Step {current_step:>6}/{total_steps} | t={time:.4e} | "
+                        f"Snapshots: {snapshot_counter}/{len(snapshot_steps)} | {rate:.1f} steps/s | "
+                        f"avg {elapsed / step_i * 1000:.1f}ms/step | ETA {eta:.0f}s")
+            if debug_energy and E_ref != 0.0:
+                KE, PE, _ = energies()          # collective: every rank takes part
+                dE = (KE + PE - E_ref) / abs(E_ref)
+                Q = KE / abs(PE) if PE != 0.0 else float("nan")
+                if line is not None:
+                    line += f" | Q={Q:.3f}  dE/E={dE:+.2e}"
+            if line is not None:
+                print(line, flush=True)
+
+        if current_step > 0 and (current_step % restart_interval) == 0:
+            xv_cpu = host_state()
+            if is_root:
+                _save_restart(xv_cpu, time, current_step, output_path, snapshot_counter, **_restart_kwargs)
+
+    if snapshot_counter < len(snapshot_steps) and snapshot_steps[-1] == total_steps:
+        if save_snapshots:
+            xv_cpu = host_state()
+            if verbose:
+                print(f"<=Saving final snapshot snap.{snapshot_counter:03d} at step {total_steps}, "
+                      f"time {time:.6e}=>")
+            if is_root:
+                _save_snapshot(xv_cpu, snapshot_counter, time, output_path, **_snap_kwargs)
+                _update_snapshot_times(output_path, snapshot_counter, time)
+        snapshot_counter += 1
+
+    xv_final_cpu = host_state()
+    if is_root:
+        _save_restart(xv_final_cpu, time, total_steps, output_path, snapshot_counter, **_restart_kwargs)
+
+    if verbose:
+        total_time = pytime.perf_counter() - t_start
+        avg = total_time / remaining_steps if remaining_steps > 0 else 0
+        print("\n" + "=" * 80)
+        print("Integration Complete")
+        print("=" * 80)
+        print(f"Final time: {time:.6e}")
+        print(f"Total wall time: {total_time:.2f} s")
+        print(f"Steps per second: {remaining_steps / total_time:.1f}" if total_time > 0 else "Steps per second: n/a")
+        print(f"Average step time: {avg * 1000:.1f} ms")
+        print(f"Snapshots saved: {snapshot_counter}")
+        print("=" * 80)
+
+    run_nbody_gpu.last_engine = eng   # for benchmarks / tests: launch counts, device state
+    return xv_final_cpu
+
+
+__all__ = ["run_nbody_gpu", "make_plummer_sphere", "G_DEFAULT", "NBODY_UNITS"]
