@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py — the reference's headline metric on B200: pairwise interactions/s (and ms/step) for the
+direct-summation path at N = 1M (BASELINE.json), 1/2/4/8 GPUs.
+
+    python bench.py --gpus N --steps K --warmup W            # this package (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # N > 1: one rank per GPU over NCCL
+
+Workload (config 3 of BASELINE.json): make_plummer_sphere(1_000_000, M_total=1e9, a=1.0, seed=42069),
+scalar softening 0.01, precision 'float32_kahan', kernel 'plummer', force AND potential.
+One "step" = one KDK leapfrog step of the whole system = one fused kick+drift+repack, the all-gather of
+the j-records (N > 1), ONE force+potential sweep over all N^2 pairs, the fix-up and the closing half kick.
+Interactions per step = N^2 (reference convention, fields.py:1317).  Total work is fixed as GPUs are
+added ("scaling": "strong").
+
+The JSON line carries, besides the driver contract keys:
+  roofline      FP32 CUDA-core roofline of the dominant kernel (the pair sweep): 20 flop/interaction
+                (BASELINE.json) x interactions per launch / CUDA-event duration of the launch, against the
+                FFMA peak measured in the same process by nb_ubench (MEASURED_PEAKS.json has no FP32 figure);
+  cpu_baseline  the oracle port of the reference's Numba path timed on this box's host cores on a bounded
+                row sample of the same workload (N = 1 only);
+  e2e           the same metric through the public host-array API (compute_nbody_forces_potential_gpu with
+                NumPy in / NumPy out): H2D of positions and D2H of acc+phi inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FLOPS_PER_INTERACTION = 20.0          # BASELINE.json convention
+FP32_PEAK_NOMINAL_TF = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x lanes x 2 x max SM clock
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--n", type=int, default=1_000_000)
+    p.add_argument("--kernel", default="plummer")
+    p.add_argument("--precision", default="float32_kahan")
+    p.add_argument("--softening", type=float, default=0.01)
+    p.add_argument("--dt", type=float, default=1e-4)
+    p.add_argument("--no-overlap", action="store_true", help="global summation order (deterministic) at N>1")
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    p.add_argument("--skip-cpu", action="store_true")
+    p.add_argument("--skip-e2e", action="store_true")
+    return p.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1])); power.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload(args):
+    import nbody_streams_b200 as nb
+
+    xv, m = nb.make_plummer_sphere(args.n, M_total=1e9, a=1.0, seed=42069)
+    return xv, m
+
+
+def cpu_sample(args, xv, m, seconds: float) -> dict:
+    """Oracle port (fast build, all host threads) on rows [0, R) of the workload vs all N."""
+    import oracle
+
+    oracle.build()
+    N = xv.shape[0]
+    pos = xv[:, :3].astype(np.float32)
+    kw = dict(kernel=args.kernel, precision="float32", fast=True)
+
+    def run(rows):
+        t0 = time.perf_counter()
+        oracle.compute_nbody_forces_cpu(pos, float(m[0]), args.softening, rows=(0, rows), **kw)
+        oracle.compute_nbody_potential_cpu(pos, float(m[0]), args.softening, rows=(0, rows), **kw)
+        return time.perf_counter() - t0
+
+    probe_rows = min(N, 256)
+    t = run(probe_rows)                                 # also warms the OpenMP pool
+    rate = probe_rows * N / max(t, 1e-9)
+    rows = int(min(N, max(probe_rows, seconds * rate / N)))
+    rows = max(1, (rows // 64) * 64) if rows >= 64 else rows
+    t = run(rows)
+    return {"value": rows * N / t, "unit": "interactions/s", "cores": oracle.num_threads(True), "kind": "port",
+            "sample": f"rows [0,{rows}) of the N={N} Plummer workload against all N, force pass + potential pass "
+                      f"({args.kernel}, float32 pair math / float64 sums as the reference CPU path), {t:.1f} s",
+            "seconds": t, "rows": rows}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    xv, m = workload(args)
+    res = []
+    per_step = max(1.0, min(args.cpu_seconds, 60.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        r = cpu_sample(args, xv, m, per_step)
+        if i >= args.warmup:
+            res.append(r)
+    val = float(np.median([r["value"] for r in res]))
+    N = xv.shape[0]
+    line = {
+        "impl": "reference", "metric": "pairwise interactions/s", "value": val, "unit": "interactions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": N * N / val * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Plummer N={N} direct {args.precision} force+potential, kernel={args.kernel}, "
+                               f"softening={args.softening} (BASELINE config 3)",
+                   "note": "reference CPU algorithm (C/OpenMP port of the Numba path; the reference is Python and "
+                           "cannot travel to the GPU box); ms_per_step extrapolates the sampled rate to N^2"},
+        "cpu_baseline": {**{k: res[-1][k] for k in ("unit", "cores", "kind", "sample")}, "value": val},
+        "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import nbody_streams_b200 as nb
+    from nbody_streams_b200 import _lib
+    from nbody_streams_b200._lib import MODE_BOTH
+    from nbody_streams_b200.engine import DirectEngine
+    from nbody_streams_b200.fields import EPS2_DEFAULT, KERNEL_MAP, _PRECISION_MAP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+
+    xv, m = workload(args)
+    N = xv.shape[0]
+    prec, dtype_np = _PRECISION_MAP[args.precision]
+    kid = KERNEL_MAP[args.kernel]
+
+    # ---- FP32 / FP64 FMA peak of THIS device, measured now (roofline denominator) ----
+    ops, ms = C.c_double(), C.c_double()
+    which = 7 if args.precision == "float64" else 0
+    _lib.check(lib.nb_ubench(which, 20000, C.byref(ops), C.byref(ms)))
+    peak_tf = 2.0 * ops.value / 1e12
+
+    eng = DirectEngine(N, float(m[0]), args.softening, prec, kid, nb.G_DEFAULT, EPS2_DEFAULT[args.precision], device,
+                       overlap=not args.no_overlap)
+    eng.load_state(xv)
+    eng.compute(MODE_BOTH, positions_changed=False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def step():
+        flush.zero_()                      # L2 flush between steps (inside the timed region, ~0.05 ms)
+        eng.kick_drift(args.dt)
+        eng.compute(MODE_BOTH)
+        eng.kick(args.dt)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.sweep_events = []
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = e0.elapsed_time(e1)
+    gpu_launches = eng.launches - launches0 + args.steps       # + the L2-flush memset per step (torch kernel)
+    sweep_ms = [a.elapsed_time(b) for a, b, _ in eng.sweep_events]
+    sweep_tiles = [t for _, _, t in eng.sweep_events]
+    eng.sweep_events = None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = args.steps * float(N) * float(N) / (elapsed_ms * 1e-3)
+
+    # roofline of the dominant kernel (the pair sweep) on this rank: flops per launch / launch duration
+    inter_per_launch = [eng.n_local * tiles * 256.0 for tiles in sweep_tiles]
+    sweep_total_ms = float(np.sum(sweep_ms))
+    achieved_tf = FLOPS_PER_INTERACTION * float(np.sum(inter_per_launch)) / (sweep_total_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp32" if args.precision != "float64" else "fp64",
+        "kernel": "nb::sweep_f32_kernel" if args.precision != "float64" else "nb::sweep_f64_kernel",
+        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+        "peak_source": "FFMA (DFMA for float64) microbenchmark nb_ubench run in this process just before the timed "
+                       "region; MEASURED_PEAKS.json carries no FP32/FP64 CUDA-core figure",
+        "peak_nominal": FP32_PEAK_NOMINAL_TF if args.precision != "float64" else FP32_PEAK_NOMINAL_TF / 2,
+        "frac_of_nominal": achieved_tf / (FP32_PEAK_NOMINAL_TF if args.precision != "float64" else FP32_PEAK_NOMINAL_TF / 2),
+        "flops_per_interaction": FLOPS_PER_INTERACTION,
+        "launch_ms_avg": sweep_total_ms / max(1, len(sweep_ms)), "launches_timed": len(sweep_ms),
+        "sweep_share_of_step": sweep_total_ms / elapsed_ms,
+        "traffic": None,
+        "traffic_note": "HBM traffic of the sweep is ~0.1 GB per launch (see profiles/): the 20 MB j-buffer is "
+                        "L2-resident; the bound is the FP32 pipe, not HBM and not tensor cores",
+    }
+
+    # ---- e2e: public host-array API, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.skip_e2e:
+        pos_host = np.ascontiguousarray(xv[:, :3].astype(dtype_np))
+        kw = dict(precision=args.precision, kernel=args.kernel)
+        if world > 1:
+            kw["group"] = dist.group.WORLD
+        nb.compute_nbody_forces_potential_gpu(pos_host, float(m[0]), args.softening, **kw)   # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            acc, phi = nb.compute_nbody_forces_potential_gpu(pos_host, float(m[0]), args.softening, **kw)
+        barrier()
+        dt_e2e = time.perf_counter() - t0
+        t = torch.tensor([dt_e2e], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_e2e = float(t.item())
+        e2e = {"value": n_e2e * float(N) * float(N) / dt_e2e, "unit": "interactions/s",
+               "h2d_bytes_per_step": int(pos_host.nbytes), "d2h_bytes_per_step": int(acc.nbytes + phi.nbytes),
+               "ms_per_call": dt_e2e / n_e2e * 1e3, "calls": n_e2e,
+               "api": "compute_nbody_forces_potential_gpu(numpy pos, scalar mass, scalar softening) -> numpy"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_sample(args, xv, m, args.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "pairwise interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if args.precision != "float64" else "f64", "data": "synthetic",
+            "config": {
+                "workload": f"Plummer N={N} direct {args.precision} force+potential, kernel={args.kernel}, "
+                            f"softening={args.softening} (BASELINE config 3)",
+                "step": "KDK leapfrog step: fused kick+drift+repack, all-gather (N>1), one force+potential sweep "
+                        "over N^2 pairs, fix-up, half kick; float64 pos/vel resident on the device",
+                "parallelism": f"i-particles sharded over {world} GPU(s), j-records all-gathered over NCCL"
+                               + (", local-shard sweep overlapped with the gather" if world > 1 and not args.no_overlap else ""),
+                "l2": "256 MiB memset between steps (inside the timed region)",
+                "tuning_variant": int(lib.nb_get_variant(prec)),
+            },
+            "fraction_of_fp32_peak": value * FLOPS_PER_INTERACTION / 1e12 / (peak_tf * world),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -171,8 +171,8 @@ int nb_tile_j(void) { return TJ; }
 int nb_block_i(int prec) { return block_i_max(prec); }
 long nb_padded_count(long n) { return ((n + TJ - 1) / TJ) * TJ; }
 size_t nb_packed_bytes(int prec, long n) {
-    const size_t np = static_cast<size_t>(nb_padded_count(n));
-    return np * (prec == NB_PREC_F64 ? 40 : 20);
+    const size_t nt = static_cast<size_t>(nb_padded_count(n)) / TJ;
+    return nt * (prec == NB_PREC_F64 ? TILE_BYTES_F64 : TILE_BYTES_F32);
 }
 
 int nb_pack(int prec, int kernel_id, void* packed, long first, const void* pos, int pos_dt, const void* mass,

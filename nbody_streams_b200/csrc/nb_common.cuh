@@ -26,8 +26,13 @@ constexpr int IB_F64 = THREADS * I_F64;
 // One tile of the packed buffer is structure-of-arrays: [x TJ][y TJ][z TJ][m TJ][c TJ].
 // SoA lets the inner loop fetch 4 (f32) / 2 (f64) j-particles per LDS.128 and lets the
 // i-pairs be fetched as aligned 64-bit (x_i, x_i+1) register pairs for FADD2/FFMA2.
-constexpr int TILE_BYTES_F32 = TJ * 20;
-constexpr int TILE_BYTES_F64 = TJ * 40;
+// Each tile ends with 16 bytes of metadata written by nb_pack: {c_uni, m_uni} (f32: 2 floats + pad,
+// f64: 2 doubles) = the common softening term / mass of the tile's 256 particles, or NaN when they
+// differ.  Tiles with uniform mass / softening take sweep paths without the per-interaction FMNMX
+// and mass multiply.  The metadata rides along with the tile's bulk copy (and the all-gather).
+constexpr int TILE_META_BYTES = 16;
+constexpr int TILE_BYTES_F32 = TJ * 20 + TILE_META_BYTES;
+constexpr int TILE_BYTES_F64 = TJ * 40 + TILE_META_BYTES;
 constexpr int COMP_X = 0, COMP_Y = 1, COMP_Z = 2, COMP_M = 3, COMP_C = 4;
 
 // ---------------------------------------------------------------------------

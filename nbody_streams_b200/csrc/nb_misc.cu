@@ -17,16 +17,17 @@ __device__ __forceinline__ double load_as_double(const void* p, int dt, long lon
     return dt == NB_DT_F64 ? static_cast<const double*>(p)[idx] : static_cast<double>(static_cast<const float*>(p)[idx]);
 }
 
+// one CTA of TJ threads per tile: SoA records + the tile's uniformity metadata
 template <typename T>
-__global__ void pack_kernel(T* __restrict__ tiles, const void* __restrict__ pos, int pos_dt,
-                            const void* __restrict__ mass, int mass_dt, double mass_scalar,
-                            const void* __restrict__ h, int h_dt, double h_scalar, long long n, long long n_pad,
-                            double eps2, int add_eps) {
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= n_pad) return;
-    const long long t = idx / TJ;
-    const int k       = static_cast<int>(idx - t * TJ);
-    T* tb = tiles + t * (TJ * 5);
+__global__ void __launch_bounds__(TJ) pack_kernel(unsigned char* __restrict__ tiles, const void* __restrict__ pos,
+                                                   int pos_dt, const void* __restrict__ mass, int mass_dt,
+                                                   double mass_scalar, const void* __restrict__ h, int h_dt,
+                                                   double h_scalar, long long n, double eps2, int add_eps) {
+    constexpr int TB = (sizeof(T) == 8) ? TILE_BYTES_F64 : TILE_BYTES_F32;
+    const long long t = blockIdx.x;
+    const int k       = threadIdx.x;
+    const long long idx = t * TJ + k;
+    T* tb = reinterpret_cast<T*>(tiles + static_cast<size_t>(t) * TB);
     T x = T(0), y = T(0), z = T(0), m = T(0), c = T(1);
     if (idx < n) {
         // cast to the kernel dtype FIRST (reference: pos.astype(dtype), run.py:188), then square h
@@ -43,6 +44,24 @@ __global__ void pack_kernel(T* __restrict__ tiles, const void* __restrict__ pos,
     tb[COMP_Z * TJ + k] = z;
     tb[COMP_M * TJ + k] = m;
     tb[COMP_C * TJ + k] = c;
+    __shared__ T first[2];
+    if (k == 0) {
+        first[0] = c;
+        first[1] = m;
+    }
+    __syncthreads();
+    const int c_same = __syncthreads_and(c == first[0]);
+    const int m_same = __syncthreads_and(m == first[1]);
+    if (k == 0) {
+        const T nan = static_cast<T>(__longlong_as_double(0x7ff8000000000000LL));
+        T* meta = tb + 5 * TJ;
+        meta[0] = c_same ? first[0] : nan;
+        meta[1] = m_same ? first[1] : nan;
+        if (sizeof(T) == 4) {
+            meta[2] = T(0);
+            meta[3] = T(0);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -125,10 +144,11 @@ __global__ void kick_drift_pack_kernel(double* __restrict__ pos, double* __restr
         pos[3 * i + d] = p[d];
     }
     if (tiles) {
+        constexpr int TB = (sizeof(T) == 8) ? TILE_BYTES_F64 : TILE_BYTES_F32;
         const long long g = first + i;
         const long long t = g / TJ;
         const int k       = static_cast<int>(g - t * TJ);
-        T* tb = tiles + t * (TJ * 5);
+        T* tb = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(tiles) + static_cast<size_t>(t) * TB);
         tb[COMP_X * TJ + k] = static_cast<T>(p[0]);
         tb[COMP_Y * TJ + k] = static_cast<T>(p[1]);
         tb[COMP_Z * TJ + k] = static_cast<T>(p[2]);
@@ -216,18 +236,16 @@ int nb_launch_pack(int prec, int kernel_id, void* packed, long long first, const
     if (n_pad <= 0) return 0;
     const int add_eps = (kernel_id == NB_KERNEL_PLUMMER || kernel_id == NB_KERNEL_DEHNEN_K1 ||
                          kernel_id == NB_KERNEL_DEHNEN_K2);
-    const int threads = 256;
-    const unsigned blocks = static_cast<unsigned>((n_pad + threads - 1) / threads);
+    const unsigned blocks = static_cast<unsigned>(n_pad / TJ);
     const long long t0 = first / TJ;
-    if (prec == NB_PREC_F64) {
-        double* tiles = static_cast<double*>(packed) + t0 * (TJ * 5);
-        pack_kernel<double><<<blocks, threads, 0, st>>>(tiles, pos, pos_dt, mass, mass_dt, mass_scalar, h, h_dt,
-                                                        h_scalar, n, n_pad, eps2, add_eps);
-    } else {
-        float* tiles = static_cast<float*>(packed) + t0 * (TJ * 5);
-        pack_kernel<float><<<blocks, threads, 0, st>>>(tiles, pos, pos_dt, mass, mass_dt, mass_scalar, h, h_dt,
-                                                       h_scalar, n, n_pad, eps2, add_eps);
-    }
+    const bool f64 = (prec == NB_PREC_F64);
+    unsigned char* tiles = static_cast<unsigned char*>(packed) + static_cast<size_t>(t0) * (f64 ? TILE_BYTES_F64 : TILE_BYTES_F32);
+    if (f64)
+        pack_kernel<double><<<blocks, TJ, 0, st>>>(tiles, pos, pos_dt, mass, mass_dt, mass_scalar, h, h_dt, h_scalar,
+                                                   n, eps2, add_eps);
+    else
+        pack_kernel<float><<<blocks, TJ, 0, st>>>(tiles, pos, pos_dt, mass, mass_dt, mass_scalar, h, h_dt, h_scalar,
+                                                  n, eps2, add_eps);
     NB_CUDA_OK(cudaGetLastError());
     return 0;
 }

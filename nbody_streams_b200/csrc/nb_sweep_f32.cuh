@@ -5,26 +5,29 @@
 // (reference nbody_streams/cuda_kernels.py:90-179, :254-366, :439-518, :591-677).
 //
 // B200 design (not a translation of the reference's 1-i-per-thread tile loop):
-//   * each thread owns NP packed PAIRS of i-particles; all pair arithmetic is
-//     issued as Blackwell packed-FP32 instructions (FADD2/FFMA2/FMUL2, sm_100+),
-//     the j-particle enters as a scalar-broadcast operand, so one warp
-//     instruction advances 64 interactions and MUFU/FMNMX/LDS issue in the
-//     slots that frees;
-//   * j-tiles are streamed into a 3-deep shared-memory ring by the TMA engine
-//     (cp.async.bulk + mbarrier, one elected thread), every lane reads the same
-//     address (broadcast LDS.128);
-//   * the grid is persistent (SMs x resident CTAs) and splits the
-//     (i-block x j-tile) work stream-K style, so every CTA does the same number
-//     of tiles whatever N is;
-//   * 'float32_kahan' is realised as compensated blocked summation: plain FFMA
-//     partial sums over one 256-particle tile, folded into FP64 running sums
-//     once per tile (the reference's CPU path also keeps f64 accumulators,
-//     fields.py:221,248-250); measured error is below the reference's
-//     per-interaction Kahan kernel at <1 % of its cost;
-//   * the self term and padding are masked only in the tiles that can contain
-//     them; the cubic spline is evaluated as a clamped Newtonian term for every
-//     pair plus an exact correction in the rare (r < h) case.
+//   * each thread owns NP packed PAIRS of i-particles held in 64-bit registers; all
+//     pair arithmetic is issued as Blackwell packed-FP32 instructions
+//     (FADD2 / FFMA2 / FMUL2, sm_100+) with the j-particle as a scalar-broadcast
+//     operand: one warp instruction advances 64 interactions;
+//   * j-tiles (structure-of-arrays, 256 particles) are streamed into a 3-deep
+//     shared-memory ring by the TMA engine (cp.async.bulk + mbarrier, one elected
+//     thread); the inner loop fetches four j-particles per broadcast LDS.128;
+//   * the grid is persistent (SMs x resident CTAs) and splits the (i-block x j-tile)
+//     work stream-K style, so every CTA does the same number of tiles whatever N is;
+//   * summation is blocked: FFMA partial sums over one tile are folded once per tile
+//     into running sums kept in shared memory — float for 'float32', DOUBLE for
+//     'float32_kahan' (compensated summation at <1 % of the cost of the reference's
+//     12 extra FADDs per interaction; the reference's own CPU path also keeps f64
+//     accumulators, fields.py:221,248-250);
+//   * nb_pack tags every tile whose 256 particles share one mass and/or one softening;
+//     such tiles skip the per-interaction FMNMX (max-softening rule hoisted per tile)
+//     and the mass multiply (applied once per tile in the fold);
+//   * the self term and padding are masked only in the tiles that can contain them;
+//     the cubic spline is a clamped Newtonian term for every pair plus an exact
+//     correction in the rare (r < h) case.
 #pragma once
+#include <type_traits>
+
 #include "nb_sweep.cuh"
 
 namespace nb {
@@ -32,39 +35,42 @@ namespace nb {
 // ---------------------------------------------------------------------------
 // one (pair of i) x (one j) interaction, packed f32x2
 //   xi,yi,zi : i positions (pair);  xj.. the j particle (scalar-broadcast operand)
-//   ci0,ci1  : per-i softening term c_i (see nb_pack); cj the j one
-//   sp       : accumulates +m/r-like terms; phi = -G * sp at the end
+//   UM : tile has one mass  -> sums are accumulated unweighted, m applied in the fold
+//   UC : tile has one softening term -> cpair = max(c_tile, c_i) precomputed per tile
+//   sp : accumulates +m/r-like terms; phi = -G * sp at the end
 // ---------------------------------------------------------------------------
-template <int KID, int MODE, bool MASK>
+template <int KID, int MODE, bool MASK, bool UM, bool UC>
 __device__ __forceinline__ void pair_f32(const float xj, const float yj, const float zj, const float mjs,
                                          const float cj, const f2 xi, const f2 yi, const f2 zi, const float ci0,
-                                         const float ci1, f2& ax, f2& ay, f2& az, f2& sp, const float eps2,
-                                         bool& inside, const bool v0, const bool v1) {
+                                         const float ci1, const f2 cpair, f2& ax, f2& ay, f2& az, f2& sp,
+                                         const float eps2, bool& inside, const bool v0, const bool v1) {
     const f2 dx = sub2(splat(xj), xi);
     const f2 dy = sub2(splat(yj), yi);
     const f2 dz = sub2(splat(zj), zi);
-    float m0 = mjs, m1 = mjs;
-    float c0, c1, h20, h21;
+    constexpr bool kUsesC = (KID == NB_KERNEL_PLUMMER || KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
+    // h2: softening term of the pair (max rule); c: start value of the r^2 FFMA chain
+    f2 h2, c;
     if (KID == NB_KERNEL_NEWTONIAN) {
-        c0 = c1 = h20 = h21 = eps2;
-    } else if (KID == NB_KERNEL_SPLINE) {
-        c0 = c1 = eps2;
-        h20 = fmaxf(cj, ci0);
-        h21 = fmaxf(cj, ci1);
+        h2 = c = splat(eps2);
     } else {
-        c0 = h20 = fmaxf(cj, ci0);
-        c1 = h21 = fmaxf(cj, ci1);
+        h2 = UC ? cpair : pk(fmaxf(cj, ci0), fmaxf(cj, ci1));
+        c  = kUsesC ? h2 : splat(eps2);
     }
-    if (MASK) {
+    f2 mj = splat(mjs);
+    if (MASK) {   // invalid lanes: zero mass, harmless distance
+        float m0 = mjs, m1 = mjs, c0, c1;
+        upk(c, c0, c1);
         if (!v0) { m0 = 0.f; c0 = 1.f; }
         if (!v1) { m1 = 0.f; c1 = 1.f; }
+        mj = pk(m0, m1);
+        c  = pk(c0, c1);
     }
-    const f2 mj = (MASK ? pk(m0, m1) : splat(mjs));
-    const f2 c  = ((KID == NB_KERNEL_NEWTONIAN || KID == NB_KERNEL_SPLINE) && !MASK) ? splat(eps2) : pk(c0, c1);
-    const f2 d  = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, c)));
+    const f2 d = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, c)));
     float d0, d1;
     upk(d, d0, d1);
     if (KID == NB_KERNEL_SPLINE) {
+        float h20, h21;
+        upk(h2, h20, h21);
         inside |= (d0 < h20) | (d1 < h21);
         d0 = fmaxf(d0, h20);   // clamp: Newtonian value at r = h for inside pairs,
         d1 = fmaxf(d1, h21);   // the exact spline correction is added by spline_fix()
@@ -72,9 +78,9 @@ __device__ __forceinline__ void pair_f32(const float xj, const float yj, const f
     const f2 rinv = pk(rsqrt_approx(d0), rsqrt_approx(d1));
 
     if (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2) {
-        const f2 mr    = mul2(mj, rinv);
+        const f2 mr    = UM ? rinv : mul2(mj, rinv);
         const f2 rinv2 = mul2(rinv, rinv);
-        const f2 t     = mul2(pk(h20, h21), rinv2);
+        const f2 t     = mul2(h2, rinv2);
         if (MODE & NB_MODE_POT) {
             f2 pf;
             if (KID == NB_KERNEL_DEHNEN_K1) pf = fma2(splat(0.5f), t, splat(1.f));
@@ -92,9 +98,9 @@ __device__ __forceinline__ void pair_f32(const float xj, const float yj, const f
         }
     } else {
         if (MODE == NB_MODE_POT) {
-            sp = fma2(mj, rinv, sp);
+            sp = UM ? add2(sp, rinv) : fma2(mj, rinv, sp);
         } else {
-            const f2 mr = mul2(mj, rinv);
+            const f2 mr = UM ? rinv : mul2(mj, rinv);
             if (MODE & NB_MODE_POT) sp = add2(sp, mr);
             const f2 rinv2 = mul2(rinv, rinv);
             const f2 f     = mul2(mr, rinv2);
@@ -105,11 +111,10 @@ __device__ __forceinline__ void pair_f32(const float xj, const float yj, const f
     }
 }
 
-// exact spline correction for one (i, j) with r < h: replaces the clamped
-// Newtonian term the packed path added by the true spline value.
-// (xi,yi,zi the i position; a* the scalar accumulators of that i.)
-template <int MODE>
-__device__ __forceinline__ void spline_fix(const float xj, const float yj, const float zj, const float mj,
+// exact spline correction for one (i, j) with r < h: replaces the clamped Newtonian term the
+// packed path added by the true spline value (UM: unweighted, like the packed path).
+template <int MODE, bool UM>
+__device__ __forceinline__ void spline_fix(const float xj, const float yj, const float zj, const float mj_in,
                                            const float cj, const float xi, const float yi, const float zi,
                                            const float ci, float& ax, float& ay, float& az, float& sp,
                                            const float eps2, const bool valid) {
@@ -117,8 +122,9 @@ __device__ __forceinline__ void spline_fix(const float xj, const float yj, const
     const float d  = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, eps2)));
     const float h2 = fmaxf(cj, ci);
     if (valid && d < h2) {
-        const float rc = rsqrt_approx(h2);   // what the packed path used: rsqrt(max(d,h2))
-        const float mr = mj * rc;
+        const float mj = UM ? 1.f : mj_in;
+        const float rc = rsqrt_approx(h2);   // what the packed path used: rsqrt(max(d, h2))
+        const float mr = UM ? rc : mj * rc;
         const float r = sqrtf(d), h = sqrtf(h2);
         if (MODE & NB_MODE_FORCE) {
             const float f_main = mr * (rc * rc);
@@ -131,7 +137,7 @@ __device__ __forceinline__ void spline_fix(const float xj, const float yj, const
     }
 }
 
-// per-thread i-state: NP packed pairs
+// per-thread i-state: NP packed pairs + their per-tile partial sums
 template <int NP>
 struct IState {
     f2 x[NP], y[NP], z[NP];        // positions (i0, i1)
@@ -142,32 +148,43 @@ struct IState {
 // ---------------------------------------------------------------------------
 // one j-tile against this thread's NP pairs
 // ---------------------------------------------------------------------------
-template <int KID, int MODE, bool MASK, int NP>
+template <int KID, int MODE, bool MASK, bool UM, bool UC, int NP>
 __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage, IState<NP>& S, const float eps2,
-                                         const long long jg0, const long long ig0, const long long n_j) {
+                                         const float c_tile, const long long jg0, const long long ig0,
+                                         const long long n_j) {
     const float* __restrict__ sX = reinterpret_cast<const float*>(stage) + COMP_X * TJ;
     const float* __restrict__ sY = reinterpret_cast<const float*>(stage) + COMP_Y * TJ;
     const float* __restrict__ sZ = reinterpret_cast<const float*>(stage) + COMP_Z * TJ;
     const float* __restrict__ sM = reinterpret_cast<const float*>(stage) + COMP_M * TJ;
     const float* __restrict__ sC = reinterpret_cast<const float*>(stage) + COMP_C * TJ;
     constexpr int JU = MASK ? 1 : 4;
+    constexpr bool kNeedC = (KID != NB_KERNEL_NEWTONIAN) && !UC;
+
+    f2 cpair[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) cpair[q] = UC ? pk(fmaxf(c_tile, S.c0[q]), fmaxf(c_tile, S.c1[q])) : 0ull;
+
 #pragma unroll 1
     for (int j0 = 0; j0 < TJ; j0 += JU) {
         float xs[4], ys[4], zs[4], ms[4], cs[4];
-        if (JU == 4) {   // five broadcast LDS.128 fetch four j-particles
+        if (JU == 4) {   // broadcast LDS.128: four j-particles per load
             const float4 x4 = *reinterpret_cast<const float4*>(sX + j0);
             const float4 y4 = *reinterpret_cast<const float4*>(sY + j0);
             const float4 z4 = *reinterpret_cast<const float4*>(sZ + j0);
-            const float4 m4 = *reinterpret_cast<const float4*>(sM + j0);
             xs[0] = x4.x; xs[1] = x4.y; xs[2] = x4.z; xs[3] = x4.w;
             ys[0] = y4.x; ys[1] = y4.y; ys[2] = y4.z; ys[3] = y4.w;
             zs[0] = z4.x; zs[1] = z4.y; zs[2] = z4.z; zs[3] = z4.w;
-            ms[0] = m4.x; ms[1] = m4.y; ms[2] = m4.z; ms[3] = m4.w;
-            if (KID != NB_KERNEL_NEWTONIAN) {
+            if (!UM) {
+                const float4 m4 = *reinterpret_cast<const float4*>(sM + j0);
+                ms[0] = m4.x; ms[1] = m4.y; ms[2] = m4.z; ms[3] = m4.w;
+            } else {
+                ms[0] = ms[1] = ms[2] = ms[3] = 1.f;
+            }
+            if (kNeedC) {
                 const float4 c4 = *reinterpret_cast<const float4*>(sC + j0);
                 cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
             } else {
-                cs[0] = cs[1] = cs[2] = cs[3] = 0.f;
+                cs[0] = cs[1] = cs[2] = cs[3] = c_tile;
             }
         } else {
             xs[0] = sX[j0]; ys[0] = sY[j0]; zs[0] = sZ[j0]; ms[0] = sM[j0]; cs[0] = sC[j0];
@@ -185,8 +202,9 @@ __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage
                     v0 = jv && (jg != ig);
                     v1 = jv && (jg != ig + 1);
                 }
-                pair_f32<KID, MODE, MASK>(xs[jj], ys[jj], zs[jj], ms[jj], cs[jj], S.x[q], S.y[q], S.z[q], S.c0[q],
-                                          S.c1[q], S.ax[q], S.ay[q], S.az[q], S.sp[q], eps2, inside, v0, v1);
+                pair_f32<KID, MODE, MASK, UM, UC>(xs[jj], ys[jj], zs[jj], ms[jj], cs[jj], S.x[q], S.y[q], S.z[q],
+                                                  S.c0[q], S.c1[q], cpair[q], S.ax[q], S.ay[q], S.az[q], S.sp[q],
+                                                  eps2, inside, v0, v1);
             }
         }
         if (KID == NB_KERNEL_SPLINE) {
@@ -209,8 +227,8 @@ __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage
                         upk(S.x[q], x0, x1); upk(S.y[q], y0, y1); upk(S.z[q], z0, z1);
                         upk(S.ax[q], ax0, ax1); upk(S.ay[q], ay0, ay1); upk(S.az[q], az0, az1);
                         upk(S.sp[q], sp0, sp1);
-                        spline_fix<MODE>(xj, yj, zj, mj, cj, x0, y0, z0, S.c0[q], ax0, ay0, az0, sp0, eps2, v0);
-                        spline_fix<MODE>(xj, yj, zj, mj, cj, x1, y1, z1, S.c1[q], ax1, ay1, az1, sp1, eps2, v1);
+                        spline_fix<MODE, UM>(xj, yj, zj, mj, cj, x0, y0, z0, S.c0[q], ax0, ay0, az0, sp0, eps2, v0);
+                        spline_fix<MODE, UM>(xj, yj, zj, mj, cj, x1, y1, z1, S.c1[q], ax1, ay1, az1, sp1, eps2, v1);
                         S.ax[q] = pk(ax0, ax1); S.ay[q] = pk(ay0, ay1); S.az[q] = pk(az0, az1);
                         S.sp[q] = pk(sp0, sp1);
                     }
@@ -222,16 +240,17 @@ __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage
 
 // ---------------------------------------------------------------------------
 // the sweep kernel
-//   ACC = 0: plain f32 running sums (NB_PREC_F32)
-//   ACC = 1: per-tile f32 partials folded into f64 running sums in shared
-//            memory (NB_PREC_F32_COMP, the 'float32_kahan' path)
+//   ACC = 0: per-tile partials folded into FLOAT running sums  (NB_PREC_F32)
+//   ACC = 1: per-tile partials folded into DOUBLE running sums (NB_PREC_F32_COMP, 'float32_kahan')
+// Running sums live in shared memory ([4][2*NP][THREADS], conflict-free) so the
+// register file is left to the pair arithmetic.
 // ---------------------------------------------------------------------------
 template <int NP, int ACC>
 struct SweepF32Smem {
     static constexpr int kStageBytes = STAGES * TILE_BYTES_F32;
-    static constexpr int kBarOff     = kStageBytes;
-    static constexpr int kRunOff     = kStageBytes + 64;
-    static constexpr int kRunBytes   = ACC ? 4 * 2 * NP * THREADS * 8 : 0;
+    static constexpr int kBarOff     = (kStageBytes + 15) & ~15;
+    static constexpr int kRunOff     = kBarOff + 64;
+    static constexpr int kRunBytes   = 4 * 2 * NP * THREADS * (ACC ? 8 : 4);
     static constexpr int kTotal      = kRunOff + kRunBytes;
 };
 
@@ -239,9 +258,10 @@ template <int KID, int MODE, int ACC, int NP, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     using L = SweepF32Smem<NP, ACC>;
+    using run_t = typename std::conditional<ACC != 0, double, float>::type;
     constexpr int IB = THREADS * 2 * NP;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-    double* run        = reinterpret_cast<double*>(smem + L::kRunOff);   // [4][2*NP][THREADS]
+    run_t* run         = reinterpret_cast<run_t*>(smem + L::kRunOff);   // [4][2*NP][THREADS]
 
     const int tid = threadIdx.x;
     const int cta = blockIdx.x, grid = gridDim.x;
@@ -300,10 +320,8 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
             }
             S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0ull;
         }
-        if (ACC) {
 #pragma unroll
-            for (int e = 0; e < 4 * 2 * NP; ++e) run[e * THREADS + tid] = 0.0;
-        }
+        for (int e = 0; e < 4 * 2 * NP; ++e) run[e * THREADS + tid] = run_t(0);
 
         for (int jl = jl0; jl < jl1; ++jl, ++k) {
             __syncthreads();   // everyone is done with tile k-1 -> its stage may be refilled
@@ -314,29 +332,41 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
             const long long jg0 = static_cast<long long>(gt) * TJ;
             const bool masked   = (jg0 + TJ > a.n_j) || (jg0 < ig_block + IB && jg0 + TJ > ig_block);
             const unsigned char* stage = smem + (k % STAGES) * TILE_BYTES_F32;
+            const float2 meta = *reinterpret_cast<const float2*>(stage + 5 * TJ * 4);   // {c_uni, m_uni} or NaN
+            const bool uc = (meta.x == meta.x), um = (meta.y == meta.y);
+            float m_fold = 1.f;
 
-            if (masked)
-                tile_f32<KID, MODE, true, NP>(stage, S, eps2, jg0, ig0, a.n_j);
-            else
-                tile_f32<KID, MODE, false, NP>(stage, S, eps2, jg0, ig0, a.n_j);
+            if (masked) {
+                tile_f32<KID, MODE, true, false, false, NP>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
+            } else if (um && uc) {
+                m_fold = meta.y;
+                tile_f32<KID, MODE, false, true, true, NP>(stage, S, eps2, meta.x, jg0, ig0, a.n_j);
+            } else if (um) {
+                m_fold = meta.y;
+                tile_f32<KID, MODE, false, true, false, NP>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
+            } else {
+                tile_f32<KID, MODE, false, false, false, NP>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
+            }
 
-            if (ACC) {   // fold this tile's f32 partials into the f64 running sums
+            // fold this tile's f32 partials (x tile mass) into the running sums
+            const run_t mf = static_cast<run_t>(m_fold);
 #pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    auto fold = [&](int comp, f2 v) {
-                        float lo, hi;
-                        upk(v, lo, hi);
-                        run[((comp * 2 * NP) + 2 * q) * THREADS + tid] += static_cast<double>(lo);
-                        run[((comp * 2 * NP) + 2 * q + 1) * THREADS + tid] += static_cast<double>(hi);
-                    };
-                    if (MODE & NB_MODE_FORCE) {
-                        fold(0, S.ax[q]);
-                        fold(1, S.ay[q]);
-                        fold(2, S.az[q]);
-                    }
-                    if (MODE & NB_MODE_POT) fold(3, S.sp[q]);
-                    S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0ull;
+            for (int q = 0; q < NP; ++q) {
+                auto fold = [&](int comp, f2 v) {
+                    float lo, hi;
+                    upk(v, lo, hi);
+                    run_t* r0 = &run[((comp * 2 * NP) + 2 * q) * THREADS + tid];
+                    run_t* r1 = &run[((comp * 2 * NP) + 2 * q + 1) * THREADS + tid];
+                    *r0 = fma(static_cast<run_t>(lo), mf, *r0);
+                    *r1 = fma(static_cast<run_t>(hi), mf, *r1);
+                };
+                if (MODE & NB_MODE_FORCE) {
+                    fold(0, S.ax[q]);
+                    fold(1, S.ay[q]);
+                    fold(2, S.az[q]);
                 }
+                if (MODE & NB_MODE_POT) fold(3, S.sp[q]);
+                S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0ull;
             }
         }
 
@@ -347,20 +377,15 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             const size_t li = base + 2 * (tid + THREADS * q);
+            auto R = [&](int comp, int half) { return run[((comp * 2 * NP) + 2 * q + half) * THREADS + tid]; };
             if (ACC) {
                 double4* dst = reinterpret_cast<double4*>(is_full ? a.full : a.part) + li;
-                dst[0] = make_double4(run[((0 * 2 * NP) + 2 * q) * THREADS + tid],
-                                      run[((1 * 2 * NP) + 2 * q) * THREADS + tid],
-                                      run[((2 * 2 * NP) + 2 * q) * THREADS + tid],
-                                      run[((3 * 2 * NP) + 2 * q) * THREADS + tid]);
-                dst[1] = make_double4(run[((0 * 2 * NP) + 2 * q + 1) * THREADS + tid],
-                                      run[((1 * 2 * NP) + 2 * q + 1) * THREADS + tid],
-                                      run[((2 * 2 * NP) + 2 * q + 1) * THREADS + tid],
-                                      run[((3 * 2 * NP) + 2 * q + 1) * THREADS + tid]);
+                dst[0] = make_double4(R(0, 0), R(1, 0), R(2, 0), R(3, 0));
+                dst[1] = make_double4(R(0, 1), R(1, 1), R(2, 1), R(3, 1));
             } else {
                 float4* dst = reinterpret_cast<float4*>(is_full ? a.full : a.part) + li;
-                dst[0] = make_float4(lo_of(S.ax[q]), lo_of(S.ay[q]), lo_of(S.az[q]), lo_of(S.sp[q]));
-                dst[1] = make_float4(hi_of(S.ax[q]), hi_of(S.ay[q]), hi_of(S.az[q]), hi_of(S.sp[q]));
+                dst[0] = make_float4(R(0, 0), R(1, 0), R(2, 0), R(3, 0));
+                dst[1] = make_float4(R(0, 1), R(1, 1), R(2, 1), R(3, 1));
             }
         }
         u += jl1 - jl0;

@@ -125,6 +125,47 @@ __global__ void __launch_bounds__(256) ubench_kernel(float* out, int iters, floa
             s += lo_of(ax[q]) + hi_of(ax[q]) + lo_of(ay[q]) + hi_of(ay[q]) + lo_of(az[q]) + hi_of(az[q]) + lo_of(sp[q]) +
                  hi_of(sp[q]);
         out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else if (WHICH >= 9 && WHICH <= 12) {
+        // co-issue probes: 12 FMA-pipe ops per group + k ops of another pipe
+        //  9: 12 FFMA2 + 2 MUFU    10: 12 FFMA2 + 4 FMNMX   11: 12 FFMA + 2 MUFU   12: 12 FFMA2 + 2 MUFU + 2 FMNMX
+        f2 a[12];
+        float s[4];
+        const f2 b = pk(1.0f + t * 1e-3f, 1.0f - t * 1e-3f), c = pk(t * 1e-3f, -t * 1e-3f);
+        const float bs = 1.0f + t * 1e-3f, cs = t * 1e-3f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) a[k] = pk(t + k, t - k);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s[k] = 1.0f + t + k;
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    if (WHICH == 11) {
+                        float lo, hi;
+                        upk(a[k], lo, hi);
+                        a[k] = pk(fmaf(lo, bs, cs), hi);
+                    } else {
+                        a[k] = fma2(a[k], b, c);
+                    }
+                }
+                if (WHICH == 9 || WHICH == 11 || WHICH == 12) {
+                    s[0] = rsqrt_approx(s[0]);
+                    s[1] = rsqrt_approx(s[1]);
+                }
+                if (WHICH == 10) {
+                    s[0] = fmaxf(-s[0], cs); s[1] = fmaxf(-s[1], bs); s[2] = fmaxf(-s[2], cs); s[3] = fmaxf(-s[3], bs);
+                }
+                if (WHICH == 12) {
+                    s[2] = fmaxf(-s[2], cs); s[3] = fmaxf(-s[3], bs);
+                }
+            }
+        }
+        float r = s[0] + s[1] + s[2] + s[3];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r += lo_of(a[k]) + hi_of(a[k]);
+        out[blockIdx.x * blockDim.x + threadIdx.x] = r;
     } else if (WHICH == 7) {   // DFMA
         double a[UB_CHAINS];
         const double b = 1.0 + t * 1e-3, c = t * 1e-3;
@@ -191,6 +232,11 @@ int nb_ubench_impl(int which, int iters, double* lane_ops_per_s, double* ms_out)
         case 6: rc = run_ubench<6>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 16.0; break;
         case 7: rc = run_ubench<7>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 8.0 * UB_CHAINS; break;
         case 8: rc = run_ubench<8>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 16.0; break;
+        // co-issue probes: report FMA-pipe lane-ops only (4 rounds x 12 ops; packed count 2)
+        case 9: rc = run_ubench<9>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 2 * 48.0; break;
+        case 10: rc = run_ubench<10>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 2 * 48.0; break;
+        case 11: rc = run_ubench<11>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 48.0; break;
+        case 12: rc = run_ubench<12>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 2 * 48.0; break;
         default: rc = NB_E_INVALID_ARG;
     }
     cudaFree(buf);

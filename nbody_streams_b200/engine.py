@@ -91,12 +91,12 @@ def group_info(group=None) -> tuple[int, int]:
     return 0, 1
 
 
-def allgather_shards(buf, layout: ShardLayout, rank: int, bytes_per_slot: int, group=None):
+def allgather_shards(buf, layout: ShardLayout, rank: int, shard_bytes: int, group=None):
     """In-place all-gather of the equal-size shards of a flat uint8 buffer
-    (shard r occupies bytes [r*S, (r+1)*S), S = layout.shard * bytes_per_slot)."""
+    (shard r occupies bytes [r*S, (r+1)*S), S = shard_bytes = whole tiles incl. their metadata)."""
     if layout.world == 1:
         return None
-    S = layout.shard * bytes_per_slot
+    S = int(shard_bytes)
     out = buf[: S * layout.world]
     inp = buf[rank * S:(rank + 1) * S]
     return _dist().all_gather_into_tensor(out, inp, group=group)
@@ -149,12 +149,12 @@ class DirectEngine:
         self.layout = ShardLayout(self.N, self.world)
         self.first = self.layout.first(self.rank)
         self.n_local = self.layout.count(self.rank)
-        self.bps = 40 if prec == PREC_F64 else 20
+        self.shard_bytes = int(self.lib.nb_packed_bytes(self.prec, self.layout.shard))
         self.dtype = torch.float64 if prec == PREC_F64 else torch.float32
         self.acc_dt = DT_F64 if prec == PREC_F64 else DT_F32
 
         with torch.cuda.device(self.device):
-            self.packed = torch.zeros(self.layout.n_slots * self.bps, dtype=torch.uint8, device=self.device)
+            self.packed = torch.zeros(self.shard_bytes * self.world, dtype=torch.uint8, device=self.device)
             self._grids = {}
             self._ws = None
             self._ws_bytes = 0
@@ -174,10 +174,26 @@ class DirectEngine:
         self._h_scalar = float(softening) if np.isscalar(softening) else 0.0
         self.mass_local = self._local_mass_tensor()
         self.launches = 0   # kernels launched by this engine (bench.py gpu_launches)
+        self.sweep_events = None   # set to [] to record (start, end) CUDA events around every sweep launch
 
     # -- helpers ------------------------------------------------------------
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _sweep(self, mode, jt0, jt1, jt2_0, jt2_1, ws, slot, grid):
+        """Launch one nb_sweep on the current stream (optionally bracketed by CUDA events)."""
+        torch = self.torch
+        ev = None
+        if self.sweep_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(self.device))
+        _lib.check(self.lib.nb_sweep(self.prec, self.kernel_id, mode, self.packed.data_ptr(), self.N,
+                                     jt0, jt1, jt2_0, jt2_1, self.first, self.n_local, self.eps2,
+                                     ws.data_ptr(), self._ws_bytes, slot, grid, self._stream()))
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(self.device))
+            self.sweep_events.append((ev[0], ev[1], (jt1 - jt0) + (jt2_1 - jt2_0)))
+        self.launches += 1
 
     def _local_mass_tensor(self):
         torch = self.torch
@@ -266,31 +282,23 @@ class DirectEngine:
             if self.world > 1 and positions_changed:
                 self.comm_stream.wait_stream(cur)          # shard records are written on `cur`
                 with torch.cuda.stream(self.comm_stream):
-                    allgather_shards(self.packed, self.layout, self.rank, self.bps, self.group)
+                    allgather_shards(self.packed, self.layout, self.rank, self.shard_bytes, self.group)
             if self.n_local > 0:
                 if self.overlap:
                     # slot 0: own shard (no dependency on the collective)
-                    _lib.check(lib.nb_sweep(self.prec, self.kernel_id, mode, self.packed.data_ptr(), self.N,
-                                            t0, t1, 0, 0, self.first, self.n_local, self.eps2,
-                                            ws.data_ptr(), self._ws_bytes, 0, grid, self._stream()))
+                    self._sweep(mode, t0, t1, 0, 0, ws, 0, grid)
                     n_jt[0] = t1 - t0
                     cur.wait_stream(self.comm_stream)
                     # slot 1: every other rank's tiles, as two ranges around mine
-                    _lib.check(lib.nb_sweep(self.prec, self.kernel_id, mode, self.packed.data_ptr(), self.N,
-                                            0, t0, t1, n_tiles, self.first, self.n_local, self.eps2,
-                                            ws.data_ptr(), self._ws_bytes, 1, grid, self._stream()))
+                    self._sweep(mode, 0, t0, t1, n_tiles, ws, 1, grid)
                     n_jt[1] = n_tiles - (t1 - t0)
                     n_sweeps = 2
-                    self.launches += 2
                 else:
                     if self.world > 1:
                         cur.wait_stream(self.comm_stream)
-                    _lib.check(lib.nb_sweep(self.prec, self.kernel_id, mode, self.packed.data_ptr(), self.N,
-                                            0, n_tiles, 0, 0, self.first, self.n_local, self.eps2,
-                                            ws.data_ptr(), self._ws_bytes, 0, grid, self._stream()))
+                    self._sweep(mode, 0, n_tiles, 0, 0, ws, 0, grid)
                     n_jt[0] = n_tiles
                     n_sweeps = 1
-                    self.launches += 1
                 _lib.check(lib.nb_finish(self.prec, self.kernel_id, mode, self.n_local, grid, n_sweeps, n_jt,
                                          ws.data_ptr(), self.G,
                                          self.acc.data_ptr() if mode & MODE_FORCE else None,

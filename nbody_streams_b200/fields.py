@@ -232,38 +232,56 @@ def _device_operand(arr_cpu, scalar, original, dtype_t, device):
     return t.contiguous(), 0.0
 
 
-def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, mode, G, eps2, dtype_np):
-    """pack + sweep + finish on the current stream.  Returns (acc|None, phi|None) torch tensors."""
+def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, mode, G, eps2, dtype_np, group=None):
+    """pack + sweep + finish on the current stream.  Returns (acc|None, phi|None) torch tensors.
+
+    With a torch.distributed `group` of more than one rank every rank packs all N particles, sweeps only
+    the i-rows of its tile-aligned shard and the rows are all-gathered, so each rank returns full arrays."""
     import torch
+
+    from .engine import ShardLayout, gather_rows, group_info
 
     lib = _lib.load()
     device = pos_t.device
     dtype_t = _np_to_torch_dtype(dtype_np)
-    acc = torch.empty((N, 3), dtype=dtype_t, device=device) if mode & MODE_FORCE else None
-    phi = torch.empty((N,), dtype=dtype_t, device=device) if mode & MODE_POT else None
+    rank, world = group_info(group) if group is not None else (0, 1)
+    layout = ShardLayout(N, world)
+    i_begin, n_i = layout.first(rank), layout.count(rank)
+    acc = torch.empty((n_i, 3), dtype=dtype_t, device=device) if mode & MODE_FORCE else None
+    phi = torch.empty((n_i,), dtype=dtype_t, device=device) if mode & MODE_POT else None
     if N == 0:
         return acc, phi
     with torch.cuda.device(device):
         grid = _grid_for(prec, kernel_id, mode, device)
         packed = _scratch(device, "packed", lib.nb_packed_bytes(prec, N))
-        ws_bytes = lib.nb_workspace_bytes(prec, N, grid, 1)
-        ws = _scratch(device, "workspace", ws_bytes)
         stream = torch.cuda.current_stream(device).cuda_stream
-        _lib.check(
-            lib.nb_direct(
-                prec, kernel_id, mode,
-                pos_t.data_ptr(), _dt_code(pos_t),
-                mass_t.data_ptr() if mass_t is not None else None, _dt_code(mass_t) if mass_t is not None else 0,
-                float(mass_scalar),
-                h_t.data_ptr() if h_t is not None else None, _dt_code(h_t) if h_t is not None else 0,
-                float(h_scalar),
-                N, float(G), float(eps2),
-                packed.data_ptr(), ws.data_ptr(), ws_bytes, grid,
-                acc.data_ptr() if acc is not None else None,
-                phi.data_ptr() if phi is not None else None,
-                stream,
-            )
-        )
+        mass_ptr, mass_dt = (mass_t.data_ptr(), _dt_code(mass_t)) if mass_t is not None else (None, 0)
+        h_ptr, h_dt = (h_t.data_ptr(), _dt_code(h_t)) if h_t is not None else (None, 0)
+        acc_ptr = acc.data_ptr() if acc is not None else None
+        phi_ptr = phi.data_ptr() if phi is not None else None
+        if world == 1:
+            ws_bytes = lib.nb_workspace_bytes(prec, N, grid, 1)
+            ws = _scratch(device, "workspace", ws_bytes)
+            _lib.check(lib.nb_direct(prec, kernel_id, mode, pos_t.data_ptr(), _dt_code(pos_t), mass_ptr, mass_dt,
+                                     float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, float(G), float(eps2),
+                                     packed.data_ptr(), ws.data_ptr(), ws_bytes, grid, acc_ptr, phi_ptr, stream))
+        else:
+            n_pad = lib.nb_padded_count(N)
+            _lib.check(lib.nb_pack(prec, kernel_id, packed.data_ptr(), 0, pos_t.data_ptr(), _dt_code(pos_t),
+                                   mass_ptr, mass_dt, float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, n_pad,
+                                   float(eps2), stream))
+            if n_i > 0:
+                ws_bytes = lib.nb_workspace_bytes(prec, n_i, grid, 1)
+                ws = _scratch(device, "workspace", ws_bytes)
+                n_tiles = C.c_int(n_pad // 256)
+                _lib.check(lib.nb_sweep(prec, kernel_id, mode, packed.data_ptr(), N, 0, n_tiles.value, 0, 0,
+                                        i_begin, n_i, float(eps2), ws.data_ptr(), ws_bytes, 0, grid, stream))
+                _lib.check(lib.nb_finish(prec, kernel_id, mode, n_i, grid, 1, C.byref(n_tiles), ws.data_ptr(),
+                                         float(G), acc_ptr, phi_ptr, stream))
+            if acc is not None:
+                acc = gather_rows(acc, layout, rank, group)
+            if phi is not None:
+                phi = gather_rows(phi, layout, rank, group)
     return acc, phi
 
 
@@ -318,6 +336,7 @@ def compute_nbody_forces_gpu(
     *,
     eps2: float | None = None,
     device=None,
+    group=None,
 ):
     """Direct-summation gravitational accelerations on the GPU.
 
@@ -333,7 +352,8 @@ def compute_nbody_forces_gpu(
 
     Keyword-only extensions (defaults reproduce the reference call): ``eps2``
     overrides the r^2 regularisation (see ``EPS2_DEFAULT``), ``device`` picks
-    the CUDA device.
+    the CUDA device, ``group`` (a torch.distributed process group, one rank per
+    GPU) shards the i-particles over its ranks and all-gathers the result.
 
     Raises ImportError without a CUDA device / built library, ValueError for
     bad shapes, precision or kernel names, RuntimeError for CUDA failures.
@@ -342,7 +362,7 @@ def compute_nbody_forces_gpu(
     ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
-    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np)
+    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np, group)
     if return_cupy:
         return acc.as_subclass(DeviceArray)
     return acc.cpu().numpy()
@@ -360,6 +380,7 @@ def compute_nbody_potential_gpu(
     *,
     eps2: float | None = None,
     device=None,
+    group=None,
 ):
     """Gravitational potential at each particle, ``phi_i = G sum_{j != i} m_j Phi(r_ij)``.
 
@@ -372,7 +393,7 @@ def compute_nbody_potential_gpu(
     ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
-    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np)
+    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np, group)
     if return_cupy:
         return phi.as_subclass(DeviceArray)
     return phi.cpu().numpy()
@@ -390,6 +411,7 @@ def compute_nbody_forces_potential_gpu(
     *,
     eps2: float | None = None,
     device=None,
+    group=None,
 ):
     """Accelerations AND potential from one fused sweep (new; the reference needs two
     O(N^2) passes, run.py:611-634).  Returns ``(acc (N,3), phi (N,))``."""
@@ -397,7 +419,7 @@ def compute_nbody_forces_potential_gpu(
     ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
-    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np)
+    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np, group)
     if return_cupy:
         return acc.as_subclass(DeviceArray), phi.as_subclass(DeviceArray)
     return acc.cpu().numpy(), phi.cpu().numpy()

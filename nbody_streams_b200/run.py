@@ -295,8 +295,9 @@ def run_nbody_gpu(
 
     def add_force_extra(total, t):
         fe = force_extra(full_pos().as_subclass(DeviceArray), full_vel().as_subclass(DeviceArray), masses, t)
-        fe = torch.as_tensor(np.asarray(fe) if not hasattr(fe, "__cuda_array_interface__") and not isinstance(fe, torch.Tensor) else fe,
-                             device=eng.device).to(torch.float64)[eng.layout.rows(eng.rank)]
+        if not isinstance(fe, torch.Tensor) and not hasattr(fe, "__cuda_array_interface__"):
+            fe = np.asarray(fe)               # host result: one H2D copy, as cp.asarray in the reference
+        fe = torch.as_tensor(fe, device=eng.device).to(torch.float64)[eng.layout.rows(eng.rank)]
         return fe.contiguous() if total is None else (total + fe).contiguous()
 
     if verbose:

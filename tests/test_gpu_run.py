@@ -1,0 +1,160 @@
+"""GPU integrator tests: run_nbody_gpu / run_simulation against the oracle's KDK loop and the golden
+runs of the reference (run_simulation(architecture='cpu', method='direct'))."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nbody_streams_b200 as nb
+
+    return nb
+
+
+def test_kdk_float64_matches_oracle_loop(nb, tmp_path):
+    xv, m = nb.make_plummer_sphere(2000, M_total=1e9, a=1.0, seed=11)
+    final = nb.run_nbody_gpu(xv, m, 0.0, 30e-4, 1e-4, 0.05, precision="float64", kernel="spline",
+                             output_dir=str(tmp_path), save_snapshots=False, verbose=False)
+    ref, _ = oracle.run_nbody_cpu_direct(xv, m, 0.0, 30e-4, 1e-4, 0.05, kernel="spline")
+    assert final.shape == (2000, 6) and final.dtype == np.float64
+    assert np.abs(final - ref).max() / np.abs(ref).max() < 1e-12
+    # the final restart file is always written (reference run.py:754-757)
+    r = np.load(tmp_path / "restart.npz")
+    assert np.array_equal(r["phase_space"], final) and int(r["step"]) == 30
+
+
+def test_c1_config_100_steps_vs_reference_golden(nb, golden, tmp_path):
+    """BASELINE config 1 (Plummer N=10k, spline h=0.05, float64, 100 KDK steps dt=1e-4): final state and
+    energy drift of the GPU run against the reference's own CPU run."""
+    g = golden("c1_plummer10k.npz")
+    xv, m = nb.make_plummer_sphere(10_000, M_total=1e9, a=1.0, seed=42069)
+    diags = []
+    res = nb.run_simulation(xv, [nb.Species.dark(10_000, mass=1e5, softening=0.05)], 0.0, 100 * 1e-4, 1e-4,
+                            architecture="gpu", method="direct", precision="float64", output_dir=str(tmp_path),
+                            save_snapshots=False, verbose=False, diagnostics=diags, diagnostics_every=50)
+    final = res["dark"]
+    ref_rows = g["final_rows"]
+    err = np.abs(final[::10] - ref_rows).max(axis=1) / np.abs(ref_rows).max()
+    assert np.quantile(err, 0.99) < 1e-11 and err.max() < 1e-8
+    E0 = float(g["ke0"] + g["pe0"])
+    dE_ref = float(g["ke1"] + g["pe1"]) - E0
+    step0, _, ke0, pe0, *_ = diags[0]
+    stepN, _, ke1, pe1, px, py, pz = diags[-1]
+    assert step0 == 0 and stepN == 100
+    assert abs(ke0 - float(g["ke0"])) / abs(E0) < 1e-12 and abs(pe0 - float(g["pe0"])) / abs(E0) < 1e-12
+    dE = (ke1 + pe1) - (ke0 + pe0)
+    assert abs(dE - dE_ref) / abs(E0) < 1e-10          # energy drift equal to the reference's (+9.9e-6)
+    assert abs(dE / E0) < 1e-4
+    p_scale = 1e9 * np.sqrt(2 * ke0 / 1e9)
+    assert np.linalg.norm([px, py, pz]) / p_scale < 1e-12   # momentum conservation
+
+
+@pytest.mark.parametrize("precision", ["float32", "float32_kahan"])
+def test_float32_run_tracks_float64_reference(nb, golden, precision, tmp_path):
+    # reference tests/test_physics.py:644-715: GPU float32_kahan trajectory vs CPU, rtol 1e-3 atol 1e-6
+    g = golden("c1_plummer10k.npz")
+    xv, m = nb.make_plummer_sphere(10_000, M_total=1e9, a=1.0, seed=42069)
+    final = nb.run_nbody_gpu(xv, m, 0.0, 100 * 1e-4, 1e-4, 0.05, precision=precision, kernel="spline",
+                             output_dir=str(tmp_path), save_snapshots=False, verbose=False)
+    ref = g["final_rows"]
+    assert np.allclose(final[::10], ref, rtol=1e-3, atol=1e-6 * np.abs(ref).max())
+
+
+def test_multispecies_run_simulation_vs_reference_golden(nb, golden, tmp_path):
+    g = golden("multispecies_n1251.npz")
+    sp = [nb.Species.dark(1000, mass=float(g["mass"][0]), softening=0.05),
+          nb.Species.star(250, mass=float(g["mass"][1000]), softening=np.linspace(0.01, 0.03, 250)),
+          nb.Species("bh", 1, 1e8, softening=0.001)]
+    res = nb.run_simulation(g["xv"], sp, 0.0, 20 * 1e-4, 1e-4, precision="float64", output_dir=str(tmp_path),
+                            save_snapshots=False, verbose=False)
+    assert list(res) == ["dark", "star", "bh"]
+    assert res["dark"].shape == (1000, 6) and res["star"].shape == (250, 6) and res["bh"].shape == (1, 6)
+    final = np.vstack([res["dark"], res["star"], res["bh"]])
+    ref = np.vstack([g["final_dark"], g["final_star"], g["final_bh"]])
+    d = np.abs(final - ref).max(axis=1) / np.abs(ref).max()
+    assert np.quantile(d, 0.99) < 1e-12 and d.max() < 1e-7   # one star orbits 0.02 kpc from the BH (chaotic)
+
+
+def test_energy_conservation_small_system(nb, tmp_path):
+    # reference tests/test_physics.py:51-62,226-244: N=80, EPS=0.2, G=1, 50 steps: |dE/E| < 1 %, momentum 1e-8
+    rng = np.random.default_rng(42)
+    N = 80
+    pos = rng.standard_normal((N, 3))
+    vel = rng.standard_normal((N, 3)) * 0.1
+    mass = np.full(N, 1.0 / N)
+    vel -= (mass[:, None] * vel).sum(0) / mass.sum()
+    xv = np.hstack([pos, vel])
+    for precision, etol in (("float64", 1e-2), ("float32_kahan", 5e-2)):
+        diags = []
+        nb.run_nbody_gpu(xv, mass, 0.0, 0.25, 5e-3, 0.2, G=1.0, precision=precision, kernel="spline",
+                         output_dir=str(tmp_path / precision), save_snapshots=False, verbose=False,
+                         diagnostics=diags, diagnostics_every=10)
+        E = np.array([d[2] + d[3] for d in diags])
+        assert np.abs(E - E[0]).max() / abs(E[0]) < etol
+        p = np.array([d[4:7] for d in diags])
+        assert np.abs(p).max() < 1e-8 if precision == "float64" else np.abs(p).max() < 1e-6
+
+
+def test_hooks_external_potential_and_force_extra(nb, tmp_path):
+    class Harmonic:   # host potential with the agama call shape: force(pos, t=) -> (N,3)
+        def force(self, pos, t=0.0):
+            return -0.5 * np.asarray(pos)
+
+    calls = []
+
+    def drag(pos, vel, masses, time):
+        calls.append(time)
+        return -0.01 * vel.get()          # reference closures call .get() on the device arrays
+
+    xv, m = nb.make_plummer_sphere(500, M_total=1e6, a=1.0, seed=3)
+    final = nb.run_nbody_gpu(xv, m, 0.0, 10e-3, 1e-3, 0.05, precision="float64", kernel="plummer",
+                             external_potential=Harmonic(), external_update_interval=1, force_extra=drag,
+                             output_dir=str(tmp_path), save_snapshots=False, verbose=False)
+    assert len(calls) == 10
+    # host restatement of the same loop (run.py:666-695)
+    x, v = xv[:, :3].copy(), xv[:, 3:].copy()
+    pot = Harmonic()
+    acc = oracle.compute_nbody_forces_cpu(x, m, 0.05, kernel="plummer") + pot.force(x)
+    t = 0.0
+    for _ in range(10):
+        v += acc * 0.5e-3
+        x += v * 1e-3
+        t += 1e-3
+        acc = oracle.compute_nbody_forces_cpu(x, m, 0.05, kernel="plummer") + pot.force(x) - 0.01 * v
+        v += acc * 0.5e-3
+    assert np.abs(final - np.hstack([x, v])).max() / np.abs(xv).max() < 1e-12
+
+
+def test_restart_continue_run(nb, tmp_path):
+    xv, m = nb.make_plummer_sphere(600, M_total=1e9, a=1.0, seed=8)
+    kw = dict(precision="float64", kernel="spline", save_snapshots=False, verbose=False)
+    full = nb.run_nbody_gpu(xv, m, 0.0, 20e-4, 1e-4, 0.05, output_dir=str(tmp_path / "a"), **kw)
+    nb.run_nbody_gpu(xv, m, 0.0, 10e-4, 1e-4, 0.05, output_dir=str(tmp_path / "b"), **kw)
+    # resume the second run to t = 20e-4 from its restart file; total_steps is recomputed from (t1 - t0)/dt
+    resumed = nb.run_nbody_gpu(xv, m, 0.0, 20e-4, 1e-4, 0.05, output_dir=str(tmp_path / "b"), continue_run=True,
+                               **kw)
+    assert np.abs(resumed - full).max() / np.abs(full).max() < 1e-13
+
+
+def test_run_error_paths(nb, tmp_path):
+    xv, m = nb.make_plummer_sphere(64, seed=1)
+    with pytest.raises(ValueError):
+        nb.run_nbody_gpu(xv[:, :5], m, 0, 1e-3, 1e-4, 0.01, output_dir=str(tmp_path))
+    with pytest.raises(ValueError):
+        nb.run_nbody_gpu(xv, m[:10], 0, 1e-3, 1e-4, 0.01, output_dir=str(tmp_path))
+    with pytest.raises(ValueError):
+        nb.run_nbody_gpu(xv, m, 0, 1e-3, 1e-4, 0.01, precision="half", output_dir=str(tmp_path))
+    sp = [nb.Species.dark(64, 1.0, 0.01)]
+    with pytest.raises(TypeError):
+        nb.run_simulation(xv, sp, 0, 1e-3, 1e-4, output_dir=str(tmp_path), save_snapshots=False, bogus_kw=1)
+    with pytest.raises(ValueError):
+        nb.run_simulation(xv, [nb.Species.dark(63, 1.0)], 0, 1e-3, 1e-4, output_dir=str(tmp_path))
+    with pytest.raises(NotImplementedError):
+        nb.run_simulation(xv, sp, 0, 1e-3, 1e-4, architecture="cpu", output_dir=str(tmp_path))
+    (tmp_path / "snapshot.h5").write_bytes(b"x")
+    with pytest.raises(FileExistsError):
+        nb.run_nbody_gpu(xv, m, 0, 1e-3, 1e-4, 0.01, output_dir=str(tmp_path), save_snapshots=True, verbose=False)

@@ -48,7 +48,8 @@ def main():
     N = arg("--n", 262144)
     # ---- peaks
     names = {0: "ffma", 1: "ffma2", 2: "ffma2_3op", 3: "fadd2", 4: "fmul2", 5: "mufu_rsq", 6: "mix_packed",
-             7: "dfma", 8: "mix_scalar"}
+             7: "dfma", 8: "mix_scalar", 9: "ffma2x12+mufu2", 10: "ffma2x12+fmnmx4", 11: "ffmax12+mufu2",
+             12: "ffma2x12+mufu2+fmnmx2"}
     ub = {}
     for which, name in names.items():
         ops, ms = C.c_double(), C.c_double()
