@@ -52,13 +52,25 @@ __global__ void __launch_bounds__(TJ) pack_kernel(unsigned char* __restrict__ ti
     __syncthreads();
     const int c_same = __syncthreads_and(c == first[0]);
     const int m_same = __syncthreads_and(m == first[1]);
+    // tile maximum of c (float tiles only: 16 B of metadata hold {c_uni, m_uni, c_max, 0})
+    __shared__ float cmax_w[TJ / 32];
+    float cm = static_cast<float>(c);
+    if (sizeof(T) == 4) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, off));
+        if ((k & 31) == 0) cmax_w[k >> 5] = cm;
+        __syncthreads();
+    }
     if (k == 0) {
         const T nan = static_cast<T>(__longlong_as_double(0x7ff8000000000000LL));
         T* meta = tb + 5 * TJ;
         meta[0] = c_same ? first[0] : nan;
         meta[1] = m_same ? first[1] : nan;
         if (sizeof(T) == 4) {
-            meta[2] = T(0);
+            float mx = cmax_w[0];
+#pragma unroll
+            for (int w = 1; w < TJ / 32; ++w) mx = fmaxf(mx, cmax_w[w]);
+            meta[2] = static_cast<T>(mx);
             meta[3] = T(0);
         }
     }

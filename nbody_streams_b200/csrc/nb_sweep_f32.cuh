@@ -148,7 +148,7 @@ struct IState {
 // ---------------------------------------------------------------------------
 // one j-tile against this thread's NP pairs
 // ---------------------------------------------------------------------------
-template <int KID, int MODE, bool MASK, bool UM, bool UC, int NP>
+template <int KID, int MODE, bool MASK, bool UM, bool UC, int NP, int JUF>
 __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage, IState<NP>& S, const float eps2,
                                          const float c_tile, const long long jg0, const long long ig0,
                                          const long long n_j) {
@@ -157,7 +157,7 @@ __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage
     const float* __restrict__ sZ = reinterpret_cast<const float*>(stage) + COMP_Z * TJ;
     const float* __restrict__ sM = reinterpret_cast<const float*>(stage) + COMP_M * TJ;
     const float* __restrict__ sC = reinterpret_cast<const float*>(stage) + COMP_C * TJ;
-    constexpr int JU = MASK ? 1 : 4;
+    constexpr int JU = MASK ? 1 : JUF;   // j-particles per loop iteration (4 or 8)
     constexpr bool kNeedC = (KID != NB_KERNEL_NEWTONIAN) && !UC;
 
     f2 cpair[NP];
@@ -166,25 +166,28 @@ __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage
 
 #pragma unroll 1
     for (int j0 = 0; j0 < TJ; j0 += JU) {
-        float xs[4], ys[4], zs[4], ms[4], cs[4];
-        if (JU == 4) {   // broadcast LDS.128: four j-particles per load
-            const float4 x4 = *reinterpret_cast<const float4*>(sX + j0);
-            const float4 y4 = *reinterpret_cast<const float4*>(sY + j0);
-            const float4 z4 = *reinterpret_cast<const float4*>(sZ + j0);
-            xs[0] = x4.x; xs[1] = x4.y; xs[2] = x4.z; xs[3] = x4.w;
-            ys[0] = y4.x; ys[1] = y4.y; ys[2] = y4.z; ys[3] = y4.w;
-            zs[0] = z4.x; zs[1] = z4.y; zs[2] = z4.z; zs[3] = z4.w;
-            if (!UM) {
-                const float4 m4 = *reinterpret_cast<const float4*>(sM + j0);
-                ms[0] = m4.x; ms[1] = m4.y; ms[2] = m4.z; ms[3] = m4.w;
-            } else {
-                ms[0] = ms[1] = ms[2] = ms[3] = 1.f;
-            }
-            if (kNeedC) {
-                const float4 c4 = *reinterpret_cast<const float4*>(sC + j0);
-                cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
-            } else {
-                cs[0] = cs[1] = cs[2] = cs[3] = c_tile;
+        float xs[8], ys[8], zs[8], ms[8], cs[8];
+        if (JU >= 4) {   // broadcast LDS.128: four j-particles per load
+#pragma unroll
+            for (int g = 0; g < JU / 4; ++g) {
+                const float4 x4 = *reinterpret_cast<const float4*>(sX + j0 + 4 * g);
+                const float4 y4 = *reinterpret_cast<const float4*>(sY + j0 + 4 * g);
+                const float4 z4 = *reinterpret_cast<const float4*>(sZ + j0 + 4 * g);
+                xs[4 * g] = x4.x; xs[4 * g + 1] = x4.y; xs[4 * g + 2] = x4.z; xs[4 * g + 3] = x4.w;
+                ys[4 * g] = y4.x; ys[4 * g + 1] = y4.y; ys[4 * g + 2] = y4.z; ys[4 * g + 3] = y4.w;
+                zs[4 * g] = z4.x; zs[4 * g + 1] = z4.y; zs[4 * g + 2] = z4.z; zs[4 * g + 3] = z4.w;
+                if (!UM) {
+                    const float4 m4 = *reinterpret_cast<const float4*>(sM + j0 + 4 * g);
+                    ms[4 * g] = m4.x; ms[4 * g + 1] = m4.y; ms[4 * g + 2] = m4.z; ms[4 * g + 3] = m4.w;
+                } else {
+                    ms[4 * g] = ms[4 * g + 1] = ms[4 * g + 2] = ms[4 * g + 3] = 1.f;
+                }
+                if (kNeedC) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(sC + j0 + 4 * g);
+                    cs[4 * g] = c4.x; cs[4 * g + 1] = c4.y; cs[4 * g + 2] = c4.z; cs[4 * g + 3] = c4.w;
+                } else {
+                    cs[4 * g] = cs[4 * g + 1] = cs[4 * g + 2] = cs[4 * g + 3] = c_tile;
+                }
             }
         } else {
             xs[0] = sX[j0]; ys[0] = sY[j0]; zs[0] = sZ[j0]; ms[0] = sM[j0]; cs[0] = sC[j0];
@@ -239,6 +242,122 @@ __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage
 }
 
 // ---------------------------------------------------------------------------
+// Cubic spline, unmasked tiles: two-phase groups.
+// The spline is exactly Newtonian for r >= h (cuda_kernels.py:64-67) and for realistic inputs ~1e-6 of
+// the pairs are inside h.  Per group of 2 j-particles x NP i-pairs: phase 1 computes the separations
+// and r^2 and keeps a running minimum (one FMNMX3 per pair of interactions); if the minimum is not
+// below the largest softening term that can apply (tile max of c_j, thread max of c_i) the group
+// finishes on the pure Newtonian path — no clamp, no per-pair compare; otherwise the whole group is
+// redone by exact_group() with the reference's piecewise polynomial.
+// ---------------------------------------------------------------------------
+template <int MODE, bool UM>
+__device__ __forceinline__ void spline_exact(const float xj, const float yj, const float zj, const float mj_in,
+                                             const float cj, const float xi, const float yi, const float zi,
+                                             const float ci, float& ax, float& ay, float& az, float& sp,
+                                             const float eps2) {
+    const float dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    const float d  = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, eps2)));
+    const float h2 = fmaxf(cj, ci);
+    const float mj = UM ? 1.f : mj_in;
+    float w, p;
+    if (d < h2) {
+        const float r = sqrtf(d), h = sqrtf(h2);
+        w = spline_w_inside<float>(r, h);
+        p = -spline_phi_inside<float>(r, h);
+    } else {
+        const float ri = rsqrt_approx(d);
+        p = ri;
+        w = ri * (ri * ri);
+    }
+    if (MODE & NB_MODE_FORCE) {
+        const float f = mj * w;
+        ax = fmaf(f, dx, ax);
+        ay = fmaf(f, dy, ay);
+        az = fmaf(f, dz, az);
+    }
+    if (MODE & NB_MODE_POT) sp = fmaf(mj, p, sp);
+}
+
+template <int MODE, bool UM, int NP>
+__device__ __forceinline__ void tile_f32_spline(const unsigned char* __restrict__ stage, IState<NP>& S,
+                                                const float eps2, const float c_max_tile) {
+    const float* __restrict__ sX = reinterpret_cast<const float*>(stage) + COMP_X * TJ;
+    const float* __restrict__ sY = reinterpret_cast<const float*>(stage) + COMP_Y * TJ;
+    const float* __restrict__ sZ = reinterpret_cast<const float*>(stage) + COMP_Z * TJ;
+    const float* __restrict__ sM = reinterpret_cast<const float*>(stage) + COMP_M * TJ;
+    const float* __restrict__ sC = reinterpret_cast<const float*>(stage) + COMP_C * TJ;
+    float h2max = c_max_tile;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) h2max = fmaxf(h2max, fmaxf(S.c0[q], S.c1[q]));
+    const f2 ceps = splat(eps2);
+
+#pragma unroll 1
+    for (int j0 = 0; j0 < TJ; j0 += 4) {
+        const float4 x4 = *reinterpret_cast<const float4*>(sX + j0);
+        const float4 y4 = *reinterpret_cast<const float4*>(sY + j0);
+        const float4 z4 = *reinterpret_cast<const float4*>(sZ + j0);
+        float4 m4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (!UM) m4 = *reinterpret_cast<const float4*>(sM + j0);
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w},
+                    zs[4] = {z4.x, z4.y, z4.z, z4.w}, ms[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {   // two groups of 2 j-particles
+            f2 dx[2][NP], dy[2][NP], dz[2][NP], d[2][NP];
+            float dmin = 3.0e38f;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    dx[jj][q] = sub2(splat(xs[2 * g + jj]), S.x[q]);
+                    dy[jj][q] = sub2(splat(ys[2 * g + jj]), S.y[q]);
+                    dz[jj][q] = sub2(splat(zs[2 * g + jj]), S.z[q]);
+                    d[jj][q]  = fma2(dx[jj][q], dx[jj][q], fma2(dy[jj][q], dy[jj][q], fma2(dz[jj][q], dz[jj][q], ceps)));
+                    float d0, d1;
+                    upk(d[jj][q], d0, d1);
+                    dmin = fminf(dmin, fminf(d0, d1));
+                }
+            if (dmin < h2max) {   // rare: some pair of this group may be inside its softening length
+#pragma unroll 1
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = j0 + 2 * g + jj;
+                    const float xj = sX[j], yj = sY[j], zj = sZ[j], mj = sM[j], cj = sC[j];
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        float x0, x1, y0, y1, z0, z1, ax0, ax1, ay0, ay1, az0, az1, sp0, sp1;
+                        upk(S.x[q], x0, x1); upk(S.y[q], y0, y1); upk(S.z[q], z0, z1);
+                        upk(S.ax[q], ax0, ax1); upk(S.ay[q], ay0, ay1); upk(S.az[q], az0, az1);
+                        upk(S.sp[q], sp0, sp1);
+                        spline_exact<MODE, UM>(xj, yj, zj, mj, cj, x0, y0, z0, S.c0[q], ax0, ay0, az0, sp0, eps2);
+                        spline_exact<MODE, UM>(xj, yj, zj, mj, cj, x1, y1, z1, S.c1[q], ax1, ay1, az1, sp1, eps2);
+                        S.ax[q] = pk(ax0, ax1); S.ay[q] = pk(ay0, ay1); S.az[q] = pk(az0, az1);
+                        S.sp[q] = pk(sp0, sp1);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        float d0, d1;
+                        upk(d[jj][q], d0, d1);
+                        const f2 rinv = pk(rsqrt_approx(d0), rsqrt_approx(d1));
+                        if (MODE == NB_MODE_POT) {
+                            S.sp[q] = UM ? add2(S.sp[q], rinv) : fma2(splat(ms[2 * g + jj]), rinv, S.sp[q]);
+                        } else {
+                            const f2 mr = UM ? rinv : mul2(splat(ms[2 * g + jj]), rinv);
+                            if (MODE & NB_MODE_POT) S.sp[q] = add2(S.sp[q], mr);
+                            const f2 f = mul2(mr, mul2(rinv, rinv));
+                            S.ax[q] = fma2(f, dx[jj][q], S.ax[q]);
+                            S.ay[q] = fma2(f, dy[jj][q], S.ay[q]);
+                            S.az[q] = fma2(f, dz[jj][q], S.az[q]);
+                        }
+                    }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // the sweep kernel
 //   ACC = 0: per-tile partials folded into FLOAT running sums  (NB_PREC_F32)
 //   ACC = 1: per-tile partials folded into DOUBLE running sums (NB_PREC_F32_COMP, 'float32_kahan')
@@ -254,7 +373,7 @@ struct SweepF32Smem {
     static constexpr int kTotal      = kRunOff + kRunBytes;
 };
 
-template <int KID, int MODE, int ACC, int NP, int MINB>
+template <int KID, int MODE, int ACC, int NP, int MINB, int JUF = 4>
 __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     using L = SweepF32Smem<NP, ACC>;
@@ -332,20 +451,27 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
             const long long jg0 = static_cast<long long>(gt) * TJ;
             const bool masked   = (jg0 + TJ > a.n_j) || (jg0 < ig_block + IB && jg0 + TJ > ig_block);
             const unsigned char* stage = smem + (k % STAGES) * TILE_BYTES_F32;
-            const float2 meta = *reinterpret_cast<const float2*>(stage + 5 * TJ * 4);   // {c_uni, m_uni} or NaN
+            const float4 meta = *reinterpret_cast<const float4*>(stage + 5 * TJ * 4);   // {c_uni|NaN, m_uni|NaN, c_max, -}
             const bool uc = (meta.x == meta.x), um = (meta.y == meta.y);
             float m_fold = 1.f;
 
-            if (masked) {
-                tile_f32<KID, MODE, true, false, false, NP>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
+            if (KID == NB_KERNEL_SPLINE && !masked) {
+                if (um) {
+                    m_fold = meta.y;
+                    tile_f32_spline<MODE, true, NP>(stage, S, eps2, meta.z);
+                } else {
+                    tile_f32_spline<MODE, false, NP>(stage, S, eps2, meta.z);
+                }
+            } else if (masked) {
+                tile_f32<KID, MODE, true, false, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
             } else if (um && uc) {
                 m_fold = meta.y;
-                tile_f32<KID, MODE, false, true, true, NP>(stage, S, eps2, meta.x, jg0, ig0, a.n_j);
+                tile_f32<KID, MODE, false, true, true, NP, JUF>(stage, S, eps2, meta.x, jg0, ig0, a.n_j);
             } else if (um) {
                 m_fold = meta.y;
-                tile_f32<KID, MODE, false, true, false, NP>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
+                tile_f32<KID, MODE, false, true, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
             } else {
-                tile_f32<KID, MODE, false, false, false, NP>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
+                tile_f32<KID, MODE, false, false, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
             }
 
             // fold this tile's f32 partials (x tile mass) into the running sums

@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) ubench_kernel(float* out, int iters, floa
 #pragma unroll 1
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int r = 0; r < 32; ++r)
 #pragma unroll
                 for (int k = 0; k < UB_CHAINS; ++k) a[k] = fmaf(a[k], b, c);
         }
@@ -166,6 +166,69 @@ __global__ void __launch_bounds__(256) ubench_kernel(float* out, int iters, floa
 #pragma unroll
         for (int k = 0; k < 12; ++k) r += lo_of(a[k]) + hi_of(a[k]);
         out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+    } else if (WHICH >= 13 && WHICH <= 15) {
+        // register-resident copy of the uniform-tile Plummer inner loop (what the sweep issues per pair of
+        // interactions): 13 = force+potential, 14 = force + potential accumulated on the FP64 pipe
+        // (F2F + DADD instead of FADD2), 15 = force only
+        f2 xi[2], yi[2], zi[2], ax[2], ay[2], az[2], sp[2];
+        double spd[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            xi[q] = pk(t + q, t - q); yi[q] = pk(2 * t + q, t - 2 * q); zi[q] = pk(t * q, -t * q);
+            ax[q] = ay[q] = az[q] = sp[q] = 0ull;
+        }
+        const f2 c = pk(1e-4f + t * 1e-6f, 1e-4f);
+        float xj = 0.3f + t, yj = 0.2f - t, zj = 0.1f + t;
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const f2 dx = sub2(splat(xj), xi[q]), dy = sub2(splat(yj), yi[q]), dz = sub2(splat(zj), zi[q]);
+                    const f2 d  = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, c)));
+                    float d0, d1;
+                    upk(d, d0, d1);
+                    const float r0 = rsqrt_approx(d0), r1 = rsqrt_approx(d1);
+                    const f2 rinv = pk(r0, r1);
+                    if (WHICH == 13) sp[q] = add2(sp[q], rinv);
+                    if (WHICH == 14) { spd[2 * q] += static_cast<double>(r0); spd[2 * q + 1] += static_cast<double>(r1); }
+                    const f2 f = mul2(rinv, mul2(rinv, rinv));
+                    ax[q] = fma2(f, dx, ax[q]); ay[q] = fma2(f, dy, ay[q]); az[q] = fma2(f, dz, az[q]);
+                }
+                xj += 1e-3f; yj -= 1e-3f; zj += 2e-3f;
+            }
+        }
+        float s = static_cast<float>(spd[0] + spd[1] + spd[2] + spd[3]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            s += lo_of(ax[q]) + hi_of(ax[q]) + lo_of(ay[q]) + hi_of(ay[q]) + lo_of(az[q]) + hi_of(az[q]) + lo_of(sp[q]) +
+                 hi_of(sp[q]);
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else if (WHICH == 16) {
+        // accumulate trios: acc_c = f * d_c + acc_c, c = x,y,z — three FFMA2 sharing the first operand
+        f2 f[4], d[4][3], acc[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[k] = pk(1e-3f * k + t, 1e-3f);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) { d[k][cc] = pk(t + k + cc, t - k); acc[k][cc] = 0ull; }
+        }
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) acc[k][cc] = fma2(f[k], d[k][cc], acc[k][cc]);
+        }
+        float s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) s += lo_of(acc[k][cc]) + hi_of(acc[k][cc]);
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     } else if (WHICH == 7) {   // DFMA
         double a[UB_CHAINS];
         const double b = 1.0 + t * 1e-3, c = t * 1e-3;
@@ -222,7 +285,7 @@ int nb_ubench_impl(int which, int iters, double* lane_ops_per_s, double* ms_out)
     int rc = 0;
     double ops_per_thread_iter = 0;   // lane-operations per thread per loop iteration
     switch (which) {
-        case 0: rc = run_ubench<0>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 8.0 * UB_CHAINS; break;
+        case 0: rc = run_ubench<0>(iters / 4 + 1, ctas, buf, &ms, 0); ops_per_thread_iter = 32.0 * UB_CHAINS; iters = iters / 4 + 1; break;
         case 1: rc = run_ubench<1>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 2 * 8.0 * UB_CHAINS; break;
         case 2: rc = run_ubench<2>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 2 * 8.0 * UB_CHAINS; break;
         case 3: rc = run_ubench<3>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 2 * 8.0 * UB_CHAINS; break;
@@ -237,6 +300,11 @@ int nb_ubench_impl(int which, int iters, double* lane_ops_per_s, double* ms_out)
         case 10: rc = run_ubench<10>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 2 * 48.0; break;
         case 11: rc = run_ubench<11>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 48.0; break;
         case 12: rc = run_ubench<12>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 2 * 48.0; break;
+        // uniform-tile inner-loop copies: INTERACTIONS per second (4 rounds x 2 pairs x 2 lanes = 16 / iter)
+        case 13: rc = run_ubench<13>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 16.0; break;
+        case 14: rc = run_ubench<14>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 16.0; break;
+        case 15: rc = run_ubench<15>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 16.0; break;
+        case 16: rc = run_ubench<16>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 2 * 48.0; break;
         default: rc = NB_E_INVALID_ARG;
     }
     cudaFree(buf);

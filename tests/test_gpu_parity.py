@@ -286,10 +286,13 @@ def test_results_independent_of_tuning_variant(nb):
     xv, m = nb.make_plummer_sphere(5000, M_total=1e9, a=1.0, seed=3)
     ref = oracle.compute_nbody_forces_cpu(xv[:, :3], m, 0.05, kernel="plummer")
     try:
-        for v in range(5):
+        pref = oracle.compute_nbody_potential_cpu(xv[:, :3], m, 0.05, kernel="plummer")
+        for v in range(6):
             lib.nb_set_variant(0, v)
-            acc = nb.compute_nbody_forces_gpu(xv[:, :3], m, 0.05, precision="float32_kahan", kernel="plummer")
-            assert rel_rms(acc, ref) <= TOL32
+            for kern, r_a, r_p in (("plummer", ref, pref),):
+                acc, phi = nb.compute_nbody_forces_potential_gpu(xv[:, :3], m, 0.05, precision="float32_kahan",
+                                                                 kernel=kern)
+                assert rel_rms(acc, r_a) <= TOL32 and rel_rms(phi, r_p) <= TOL32
         for v in range(3):
             lib.nb_set_variant(2, v)
             acc = nb.compute_nbody_forces_gpu(xv[:, :3], m, 0.05, precision="float64", kernel="plummer")

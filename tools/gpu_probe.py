@@ -49,11 +49,12 @@ def main():
     # ---- peaks
     names = {0: "ffma", 1: "ffma2", 2: "ffma2_3op", 3: "fadd2", 4: "fmul2", 5: "mufu_rsq", 6: "mix_packed",
              7: "dfma", 8: "mix_scalar", 9: "ffma2x12+mufu2", 10: "ffma2x12+fmnmx4", 11: "ffmax12+mufu2",
-             12: "ffma2x12+mufu2+fmnmx2"}
+             12: "ffma2x12+mufu2+fmnmx2", 13: "loop_both_uni", 14: "loop_both_uni_dadd", 15: "loop_force_uni",
+             16: "ffma2_trio_shared_f"}
     ub = {}
     for which, name in names.items():
         ops, ms = C.c_double(), C.c_double()
-        _lib.check(lib.nb_ubench(which, 20000 if which not in (6, 8) else 40000, C.byref(ops), C.byref(ms)))
+        _lib.check(lib.nb_ubench(which, 40000 if which in (6, 8, 13, 14, 15) else 20000, C.byref(ops), C.byref(ms)))
         ub[name] = {"per_s": ops.value, "ms": ms.value}
         print(name, f"{ops.value:.4e}/s", f"{ms.value:.2f} ms", flush=True)
     out["ubench"] = ub
@@ -62,7 +63,7 @@ def main():
     pos_t = torch.from_numpy(xv[:, :3].astype(np.float32)).cuda()
     pos64 = torch.from_numpy(np.ascontiguousarray(xv[:, :3])).cuda()
     res = {}
-    for v in range(5):
+    for v in ([int(x) for x in arg('--variants', '0,5,6,7').split(',')]):
         lib.nb_set_variant(0, v)
         for kernel in ("plummer", "spline"):
             for prec in ("float32", "float32_kahan"):
@@ -77,7 +78,7 @@ def main():
                     res[f"v{v}_{kernel}_{prec}_{mname}"] = {"ms": ms, "gint_s": gi}
                     print(f"v{v} {kernel:8s} {prec:14s} {mname:5s} {ms:9.3f} ms  {gi:9.1f} Gint/s", flush=True)
     lib.nb_set_variant(0, 0)
-    for v in range(3):
+    for v in range(1):
         lib.nb_set_variant(2, v)
         for kernel in ("plummer", "spline"):
             for mode, mname in ((1, "force"), (3, "both")):
