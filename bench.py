@@ -40,6 +40,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FLOPS_PER_INTERACTION = 20.0          # BASELINE.json convention
+print_json = None
 FP32_PEAK_NOMINAL_TF = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x lanes x 2 x max SM clock
 
 
@@ -115,6 +116,7 @@ def cpu_sample(args, xv, m, seconds: float) -> dict:
     import oracle
 
     oracle.build()
+    oracle.set_num_threads(len(os.sched_getaffinity(0)), fast=True)   # all host cores (torchrun sets OMP_NUM_THREADS=1)
     N = xv.shape[0]
     pos = xv[:, :3].astype(np.float32)
     kw = dict(kernel=args.kernel, precision="float32", fast=True)
@@ -162,11 +164,16 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print_json(line)
 
 
 def main():
     args = parse()
+    # keep stdout for the ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global print_json
+    print_json = lambda line: (json_out.write(json.dumps(line) + "\n"), json_out.flush())  # noqa: E731
     if args.impl == "reference":
         run_reference(args)
         return
@@ -312,7 +319,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        print_json(line)
     if world > 1:
         dist.destroy_process_group()
 

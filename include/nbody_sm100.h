@@ -86,11 +86,14 @@ int nb_device_info(int *sm_count, int *cc_major, int *cc_minor,
 /* Particles live on the device in a tile-major "packed" buffer that is both
  * the j-source the sweeps stream through shared memory (one bulk async copy
  * per tile) and the place i-particles are read from.  One tile holds
- * nb_tile_j() particles:
- *     f32 precisions: [TJ x float4 (x,y,z,m)] [TJ x float  c]   = 20 B/particle
- *     f64 precision : [TJ x double2 (x,y)] [TJ x double2 (z,m)] [TJ x double c] = 40 B/particle
+ * nb_tile_j() = 256 particles, structure-of-arrays inside the tile, followed by
+ * 16 bytes of tile metadata:
+ *     f32 precisions: [x][y][z][m][c] x 256 floats  + {c_uni, m_uni, c_max, 0}  = 5136 B
+ *     f64 precision : [x][y][z][m][c] x 256 doubles + {c_uni, m_uni}            = 10256 B
  * c = h^2 (+ eps2 for kernels 1..3): the softening term the pair kernel takes
- * the max of (max-softening rule, reference cuda_kernels.py:150).
+ * the max of (max-softening rule, reference cuda_kernels.py:150).  c_uni / m_uni
+ * are the common c / mass of the tile or NaN when its particles differ (tiles
+ * with uniform values take faster sweep paths).
  * Padding particles (index >= n) have m = 0. */
 int    nb_tile_j(void);
 int    nb_block_i(int prec);                       /* i-particles per CTA work unit  */
@@ -121,7 +124,9 @@ size_t nb_workspace_bytes(int prec, long n_i, int grid, int n_sweeps);
  * accumulate the pair sums over the j-tiles [jt_begin, jt_end) U
  * [jt2_begin, jt2_end) of `packed` (the second range may be empty; used to
  * sweep "everything but my own shard" while an all-gather is in flight).
- * n_j is the number of REAL particles in `packed` (j >= n_j is padding).
+ * n_j is the number of REAL particles in `packed` (j >= n_j is padding; tile
+ * ranges may include all-padding tiles as long as they lie inside the buffer
+ * the caller allocated and nb_pack filled).
  * Partial sums go to slot `slot` of the workspace; nb_finish() combines slots.
  * Work is split stream-K style over `grid` persistent CTAs. */
 int nb_sweep(int prec, int kernel_id, int mode,

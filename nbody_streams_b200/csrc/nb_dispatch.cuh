@@ -47,7 +47,8 @@ inline int run_f32(int op, const SweepArgs* a, int grid, int* out, cudaStream_t 
 template <int KID, int MODE, int V>
 inline int run_f64(int op, const SweepArgs* a, int grid, int* out, cudaStream_t st) {
     constexpr VariantF64 v = variant_f64(V);
-    return run_kernel(sweep_f64_kernel<KID, MODE, v.ni, v.minb>, STAGES * TILE_BYTES_F64 + 64, op, a, grid, out, st);
+    return run_kernel(sweep_f64_kernel<KID, MODE, v.ni, v.minb>, STAGES * TILE_BYTES_F64 + 64 + 4 * v.ni * THREADS * 8, op, a,
+                      grid, out, st);
 }
 
 template <int KID, int MODE, int ACC, bool ALLV>

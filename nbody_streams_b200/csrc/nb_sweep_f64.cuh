@@ -12,21 +12,24 @@
 
 namespace nb {
 
-template <int KID, int MODE, bool MASK>
+//   UM : tile has one mass (sums accumulated unweighted, m applied in the per-tile fold)
+//   UC : tile has one softening term; cmax = max(c_tile, c_i) precomputed per tile
+template <int KID, int MODE, bool MASK, bool UM, bool UC>
 __device__ __forceinline__ void pair_f64(const double xj, const double yj, const double zj, double mj,
                                          const double cj, const double xi, const double yi, const double zi,
-                                         const double ci, double& ax, double& ay, double& az, double& sp,
-                                         const double eps2, const bool valid) {
+                                         const double ci, const double cmax, double& ax, double& ay, double& az,
+                                         double& sp, const double eps2, const bool valid) {
     const double dx = xj - xi, dy = yj - yi, dz = zj - zi;
     double c, h2;
     if (KID == NB_KERNEL_NEWTONIAN) {
         c = h2 = eps2;
     } else if (KID == NB_KERNEL_SPLINE) {
         c  = eps2;
-        h2 = fmax(cj, ci);
+        h2 = UC ? cmax : fmax(cj, ci);
     } else {
-        c = h2 = fmax(cj, ci);
+        c = h2 = UC ? cmax : fmax(cj, ci);
     }
+    if (UM) mj = 1.0;
     if (MASK && !valid) {
         mj = 0.0;
         c  = 1.0;
@@ -38,7 +41,7 @@ __device__ __forceinline__ void pair_f64(const double xj, const double yj, const
         d = fmax(d, h2);
     }
     const double rinv = rsqrt_f64(d);
-    const double mr   = mj * rinv;
+    const double mr   = (UM && !MASK) ? rinv : mj * rinv;
     if (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2) {
         const double rinv2 = rinv * rinv;
         const double t     = h2 * rinv2;
@@ -80,23 +83,27 @@ struct IState64 {
     double ax[NI], ay[NI], az[NI], sp[NI];
 };
 
-template <int KID, int MODE, bool MASK, int NI>
+template <int KID, int MODE, bool MASK, bool UM, bool UC, int NI>
 __device__ __forceinline__ void tile_f64(const unsigned char* __restrict__ stage, IState64<NI>& S,
-                                         const double eps2, const long long jg0, const long long ig0,
-                                         const long long n_j) {
+                                         const double eps2, const double c_tile, const long long jg0,
+                                         const long long ig0, const long long n_j) {
     const double* __restrict__ sX = reinterpret_cast<const double*>(stage) + COMP_X * TJ;
     const double* __restrict__ sY = reinterpret_cast<const double*>(stage) + COMP_Y * TJ;
     const double* __restrict__ sZ = reinterpret_cast<const double*>(stage) + COMP_Z * TJ;
     const double* __restrict__ sM = reinterpret_cast<const double*>(stage) + COMP_M * TJ;
     const double* __restrict__ sC = reinterpret_cast<const double*>(stage) + COMP_C * TJ;
+    double cmax[NI];
+#pragma unroll
+    for (int q = 0; q < NI; ++q) cmax[q] = UC ? fmax(c_tile, S.c[q]) : 0.0;
 #pragma unroll 1
     for (int j0 = 0; j0 < TJ; j0 += 2) {
         const double2 x2 = *reinterpret_cast<const double2*>(sX + j0);
         const double2 y2 = *reinterpret_cast<const double2*>(sY + j0);
         const double2 z2 = *reinterpret_cast<const double2*>(sZ + j0);
-        const double2 m2 = *reinterpret_cast<const double2*>(sM + j0);
+        double2 m2 = make_double2(1.0, 1.0);
+        if (!UM) m2 = *reinterpret_cast<const double2*>(sM + j0);
         double2 c2 = make_double2(0.0, 0.0);
-        if (KID != NB_KERNEL_NEWTONIAN) c2 = *reinterpret_cast<const double2*>(sC + j0);
+        if (KID != NB_KERNEL_NEWTONIAN && !UC) c2 = *reinterpret_cast<const double2*>(sC + j0);
 #pragma unroll
         for (int q = 0; q < NI; ++q) {
             bool v0 = true, v1 = true;
@@ -106,10 +113,10 @@ __device__ __forceinline__ void tile_f64(const unsigned char* __restrict__ stage
                 v0 = (jg < n_j) && (jg != ig);
                 v1 = (jg + 1 < n_j) && (jg + 1 != ig);
             }
-            pair_f64<KID, MODE, MASK>(x2.x, y2.x, z2.x, m2.x, c2.x, S.x[q], S.y[q], S.z[q], S.c[q], S.ax[q], S.ay[q],
-                                      S.az[q], S.sp[q], eps2, v0);
-            pair_f64<KID, MODE, MASK>(x2.y, y2.y, z2.y, m2.y, c2.y, S.x[q], S.y[q], S.z[q], S.c[q], S.ax[q], S.ay[q],
-                                      S.az[q], S.sp[q], eps2, v1);
+            pair_f64<KID, MODE, MASK, UM, UC>(x2.x, y2.x, z2.x, m2.x, c2.x, S.x[q], S.y[q], S.z[q], S.c[q], cmax[q],
+                                              S.ax[q], S.ay[q], S.az[q], S.sp[q], eps2, v0);
+            pair_f64<KID, MODE, MASK, UM, UC>(x2.y, y2.y, z2.y, m2.y, c2.y, S.x[q], S.y[q], S.z[q], S.c[q], cmax[q],
+                                              S.ax[q], S.ay[q], S.az[q], S.sp[q], eps2, v1);
         }
     }
 }
@@ -119,6 +126,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int IB = THREADS * NI;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * TILE_BYTES_F64);
+    double* run        = reinterpret_cast<double*>(smem + STAGES * TILE_BYTES_F64 + 64);   // [4][NI][THREADS]
 
     const int tid = threadIdx.x;
     const int cta = blockIdx.x, grid = gridDim.x;
@@ -174,6 +182,8 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
             }
             S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0.0;
         }
+#pragma unroll
+        for (int e = 0; e < 4 * NI; ++e) run[e * THREADS + tid] = 0.0;
 
         for (int jl = jl0; jl < jl1; ++jl, ++k) {
             __syncthreads();
@@ -184,10 +194,32 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
             const long long jg0 = static_cast<long long>(gt) * TJ;
             const bool masked   = (jg0 + TJ > a.n_j) || (jg0 < ig_block + IB && jg0 + TJ > ig_block);
             const unsigned char* stage = smem + (k % STAGES) * TILE_BYTES_F64;
-            if (masked)
-                tile_f64<KID, MODE, true, NI>(stage, S, eps2, jg0, ig0, a.n_j);
-            else
-                tile_f64<KID, MODE, false, NI>(stage, S, eps2, jg0, ig0, a.n_j);
+            const double2 meta = *reinterpret_cast<const double2*>(stage + 5 * TJ * 8);   // {c_uni, m_uni} or NaN
+            const bool uc = (meta.x == meta.x), um = (meta.y == meta.y);
+            double m_fold = 1.0;
+            if (masked) {
+                tile_f64<KID, MODE, true, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j);
+            } else if (um && uc) {
+                m_fold = meta.y;
+                tile_f64<KID, MODE, false, true, true, NI>(stage, S, eps2, meta.x, jg0, ig0, a.n_j);
+            } else if (um) {
+                m_fold = meta.y;
+                tile_f64<KID, MODE, false, true, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j);
+            } else {
+                tile_f64<KID, MODE, false, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j);
+            }
+            // fold the tile's partial sums (x tile mass) into the running sums in shared memory
+#pragma unroll
+            for (int q = 0; q < NI; ++q) {
+                if (MODE & NB_MODE_FORCE) {
+                    run[(0 * NI + q) * THREADS + tid] = fma(S.ax[q], m_fold, run[(0 * NI + q) * THREADS + tid]);
+                    run[(1 * NI + q) * THREADS + tid] = fma(S.ay[q], m_fold, run[(1 * NI + q) * THREADS + tid]);
+                    run[(2 * NI + q) * THREADS + tid] = fma(S.az[q], m_fold, run[(2 * NI + q) * THREADS + tid]);
+                }
+                if (MODE & NB_MODE_POT)
+                    run[(3 * NI + q) * THREADS + tid] = fma(S.sp[q], m_fold, run[(3 * NI + q) * THREADS + tid]);
+                S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0.0;
+            }
         }
 
         const bool is_full = (jl0 == 0 && jl1 == a.n_jt);
@@ -195,7 +227,9 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
                                      : (static_cast<size_t>(cta) * 2 + (u == u0 ? 0 : 1)) * IB;
         double4* dst = reinterpret_cast<double4*>(is_full ? a.full : a.part) + base;
 #pragma unroll
-        for (int q = 0; q < NI; ++q) dst[tid + THREADS * q] = make_double4(S.ax[q], S.ay[q], S.az[q], S.sp[q]);
+        for (int q = 0; q < NI; ++q)
+            dst[tid + THREADS * q] = make_double4(run[(0 * NI + q) * THREADS + tid], run[(1 * NI + q) * THREADS + tid],
+                                                  run[(2 * NI + q) * THREADS + tid], run[(3 * NI + q) * THREADS + tid]);
         u += jl1 - jl0;
     }
 }

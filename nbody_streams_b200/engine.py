@@ -8,7 +8,7 @@ whole packed j-buffer (20 B/particle f32, 40 B f64).  Per step:
     kick+drift+repack own shard (1 fused kernel)
       -> all-gather of the packed shards on a side stream, in place
       -> overlap mode : sweep own j-tiles now, the remote tiles once the gather lands
-         deterministic: one sweep over all tiles in global order after the gather
+         overlap=False: one sweep over all tiles in global j order after the gather
       -> finish (fixed-order fix-up, x G)
       -> half kick
 
@@ -131,8 +131,9 @@ class DirectEngine:
     device : torch CUDA device of this rank.
     group : torch.distributed process group (None = default group / single process).
     overlap : sweep the local j-shard while the all-gather is in flight (default);
-              False sweeps all tiles in global order after the gather (bitwise equal
-              to the 1-GPU summation order).
+              False sweeps all tiles in global (j-ascending) order after the gather.
+              Either way results are bitwise reproducible for a given rank count and agree
+              with the 1-GPU result to rounding (the stream-K pieces are cut at other tiles).
     """
 
     def __init__(self, N, mass, softening, prec, kernel_id, G, eps2, device, group=None, overlap=True):

@@ -67,6 +67,12 @@ def num_threads(fast: bool = False) -> int:
     return int(getattr(lib, "nbo_num_threads" + sfx)())
 
 
+def set_num_threads(n: int, fast: bool = False) -> None:
+    """Override OMP_NUM_THREADS (torchrun exports 1) for the timing legs."""
+    lib, sfx = _lib(fast)
+    getattr(lib, "nbo_set_num_threads" + sfx)(int(n))
+
+
 def _prepare(pos, mass, softening, precision, kernel):
     """Host-side validation + scalar broadcast, as reference fields.py:485-565 and :618-658."""
     key = precision.lower()

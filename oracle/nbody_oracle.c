@@ -307,6 +307,15 @@ void NBO_NAME(nbo_potential_f32)(const float* pos, const float* mass, const floa
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the timing legs ask for all host cores explicitly */
+void NBO_NAME(nbo_set_num_threads)(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int NBO_NAME(nbo_num_threads)(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
