@@ -265,9 +265,11 @@ def main():
         "flops_per_interaction": FLOPS_PER_INTERACTION,
         "launch_ms_avg": sweep_total_ms / max(1, len(sweep_ms)), "launches_timed": len(sweep_ms),
         "sweep_share_of_step": sweep_total_ms / elapsed_ms,
-        "traffic": None,
-        "traffic_note": "HBM traffic of the sweep is ~0.1 GB per launch (see profiles/): the 20 MB j-buffer is "
-                        "L2-resident; the bound is the FP32 pipe, not HBM and not tensor cores",
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture of this
+        # command at the default workload (profiles/r01_ncu_sweep_f32_bench_n1m.md); null for other shapes
+        "traffic": 23734272 if (N == 1_000_000 and world == 1 and args.precision != "float64") else None,
+        "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic bytes per launch: 20 MB read + 32 MB "
+                        "partial sums written (absorbed by L2) for 2e13 algorithmic flop -> FP32-pipe bound",
     }
 
     # ---- e2e: public host-array API, H2D + D2H inside the timed region ----
