@@ -58,6 +58,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// arrive and learn how many arrivals were still pending BEFORE this one (1 => we completed the phase)
+__device__ __forceinline__ uint32_t mbar_arrive_pending(uint64_t* bar) {
+    uint64_t state;
+    uint32_t cnt;
+    asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(cnt) : "l"(state));
+    return cnt;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"

@@ -10,13 +10,13 @@ namespace nb {
 enum { OP_LAUNCH = 0, OP_QUERY = 1 };
 
 // tuning variants: (i-pairs per thread NP, min resident CTAs per SM)
-struct VariantF32 { int np, minb, ju; };
+struct VariantF32 { int np, minb, ju; bool dec; };
 struct VariantF64 { int ni, minb; };
 constexpr int NV_F32 = 6;
 constexpr int NV_F64 = 3;
 __host__ __device__ constexpr VariantF32 variant_f32(int v) {
-    return v == 1 ? VariantF32{2, 4, 4} : v == 2 ? VariantF32{2, 6, 4} : v == 3 ? VariantF32{3, 4, 4}
-         : v == 4 ? VariantF32{4, 3, 4} : v == 5 ? VariantF32{2, 5, 8} : VariantF32{2, 5, 4};
+    return v == 1 ? VariantF32{2, 4, 4, false} : v == 2 ? VariantF32{2, 6, 4, false} : v == 3 ? VariantF32{3, 4, 4, false}
+         : v == 4 ? VariantF32{4, 3, 4, false} : v == 5 ? VariantF32{2, 5, 4, true} : VariantF32{2, 5, 4, false};
 }
 __host__ __device__ constexpr VariantF64 variant_f64(int v) {
     return v == 1 ? VariantF64{4, 3} : v == 2 ? VariantF64{2, 5} : VariantF64{2, 4};
@@ -41,7 +41,7 @@ inline int run_kernel(K kern, int smem, int op, const SweepArgs* a, int grid, in
 template <int KID, int MODE, int ACC, int V>
 inline int run_f32(int op, const SweepArgs* a, int grid, int* out, cudaStream_t st) {
     constexpr VariantF32 v = variant_f32(V);
-    return run_kernel(sweep_f32_kernel<KID, MODE, ACC, v.np, v.minb, v.ju>, SweepF32Smem<v.np, ACC>::kTotal, op, a, grid,
+    return run_kernel(sweep_f32_kernel<KID, MODE, ACC, v.np, v.minb, v.ju, v.dec>, SweepF32Smem<v.np, ACC>::kTotal, op, a, grid,
                       out, st);
 }
 template <int KID, int MODE, int V>

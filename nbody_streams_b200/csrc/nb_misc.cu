@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(TJ) pack_kernel(unsigned char* __restrict__ ti
     const int k       = threadIdx.x;
     const long long idx = t * TJ + k;
     T* tb = reinterpret_cast<T*>(tiles + static_cast<size_t>(t) * TB);
-    T x = T(0), y = T(0), z = T(0), m = T(0), c = T(1);
+    T x = T(0), y = T(0), z = T(0), m = T(0), c = T(0);   // padding: zero mass, zero softening
     if (idx < n) {
         // cast to the kernel dtype FIRST (reference: pos.astype(dtype), run.py:188), then square h
         x = static_cast<T>(load_as_double(pos, pos_dt, 3 * idx + 0));

@@ -57,13 +57,15 @@ __device__ __forceinline__ void pair_f32(const float xj, const float yj, const f
         c  = kUsesC ? h2 : splat(eps2);
     }
     f2 mj = splat(mjs);
-    if (MASK) {   // invalid lanes: zero mass, harmless distance
-        float m0 = mjs, m1 = mjs, c0, c1;
+    if (MASK) {   // invalid lanes (self pair, padding): zero mass, harmless distance, never "inside h"
+        float m0 = mjs, m1 = mjs, c0, c1, g0, g1;
         upk(c, c0, c1);
-        if (!v0) { m0 = 0.f; c0 = 1.f; }
-        if (!v1) { m1 = 0.f; c1 = 1.f; }
+        upk(h2, g0, g1);
+        if (!v0) { m0 = 0.f; c0 = 1.f; g0 = 0.f; }
+        if (!v1) { m1 = 0.f; c1 = 1.f; g1 = 0.f; }
         mj = pk(m0, m1);
         c  = pk(c0, c1);
+        if (KID == NB_KERNEL_SPLINE) h2 = pk(g0, g1);
     }
     const f2 d = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, c)));
     float d0, d1;
@@ -373,14 +375,19 @@ struct SweepF32Smem {
     static constexpr int kTotal      = kRunOff + kRunBytes;
 };
 
-template <int KID, int MODE, int ACC, int NP, int MINB, int JUF = 4>
+//   DEC = false: one __syncthreads per tile frees the previous stage, thread 0 refills it
+//   DEC = true : warps run decoupled — every warp arrives on the stage's "empty" mbarrier when it is
+//                done with a tile and the LAST warp out (pending count 1) issues the TMA refill, so no
+//                thread ever waits for another warp except through data availability
+template <int KID, int MODE, int ACC, int NP, int MINB, int JUF = 4, bool DEC = false>
 __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     using L = SweepF32Smem<NP, ACC>;
     using run_t = typename std::conditional<ACC != 0, double, float>::type;
     constexpr int IB = THREADS * 2 * NP;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-    run_t* run         = reinterpret_cast<run_t*>(smem + L::kRunOff);   // [4][2*NP][THREADS]
+    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    uint64_t* empty_bar = full_bar + STAGES;
+    run_t* run          = reinterpret_cast<run_t*>(smem + L::kRunOff);   // [4][2*NP][THREADS]
 
     const int tid = threadIdx.x;
     const int cta = blockIdx.x, grid = gridDim.x;
@@ -391,7 +398,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], THREADS / 32);
+        }
         mbar_fence_init();
     }
     __syncthreads();
@@ -406,7 +416,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
                  TILE_BYTES_F32, bar);
     };
     if (tid == 0) {
-        for (int k = 0; k < STAGES - 1 && k < n_units; ++k) issue(k);
+        for (int k = 0; k < (DEC ? STAGES : STAGES - 1) && k < n_units; ++k) issue(k);
     }
 
     long long u = u0;
@@ -425,7 +435,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
         for (int q = 0; q < NP; ++q) {
             const long long ig = ig0 + 2LL * THREADS * q;   // even; ig+1 is in the same tile
             S.x[q] = S.y[q] = S.z[q] = 0ull;
-            S.c0[q] = S.c1[q] = 1.f;
+            S.c0[q] = S.c1[q] = 0.f;   // dummy i beyond the buffer: results are discarded
             if (ig < a.n_pad) {   // aligned 64-bit loads give (i, i+1) register pairs directly
                 const long long t = ig / TJ;
                 const int kk      = static_cast<int>(ig - t * TJ);
@@ -443,8 +453,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
         for (int e = 0; e < 4 * 2 * NP; ++e) run[e * THREADS + tid] = run_t(0);
 
         for (int jl = jl0; jl < jl1; ++jl, ++k) {
-            __syncthreads();   // everyone is done with tile k-1 -> its stage may be refilled
-            if (tid == 0 && k + STAGES - 1 < n_units) issue(k + STAGES - 1);
+            if (!DEC) {
+                __syncthreads();   // everyone is done with tile k-1 -> its stage may be refilled
+                if (tid == 0 && k + STAGES - 1 < n_units) issue(k + STAGES - 1);
+            }
             mbar_wait(&full_bar[k % STAGES], (k / STAGES) & 1);
 
             const int gt        = local_to_global_tile(a, jl);
@@ -493,6 +505,13 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
                 }
                 if (MODE & NB_MODE_POT) fold(3, S.sp[q]);
                 S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0ull;
+            }
+            if (DEC) {   // release the stage; the last warp out refills it with the tile STAGES ahead
+                __syncwarp();
+                if ((tid & 31) == 0) {
+                    const uint32_t pending = mbar_arrive_pending(&empty_bar[k % STAGES]);
+                    if (pending == 1 && k + STAGES < n_units) issue(k + STAGES);
+                }
             }
         }
 

@@ -30,9 +30,10 @@ __device__ __forceinline__ void pair_f64(const double xj, const double yj, const
         c = h2 = UC ? cmax : fmax(cj, ci);
     }
     if (UM) mj = 1.0;
-    if (MASK && !valid) {
+    if (MASK && !valid) {   // self pair / padding: zero mass, harmless distance, never "inside h"
         mj = 0.0;
         c  = 1.0;
+        if (KID == NB_KERNEL_SPLINE) h2 = 0.0;
     }
     double d = fma(dx, dx, fma(dy, dy, fma(dz, dz, c)));
     bool inside = false;
@@ -121,6 +122,103 @@ __device__ __forceinline__ void tile_f64(const unsigned char* __restrict__ stage
     }
 }
 
+// ---------------------------------------------------------------------------
+// Cubic spline, unmasked tiles, two-phase groups (same idea as tile_f32_spline): phase 1 computes the
+// separations and r^2 of a group (2 j x NI i) and tracks the minimum r^2 through the HIGH 32-bit word of
+// the doubles (monotonic for positive values; one integer min per interaction instead of an emulated
+// double fmin); if that minimum cannot be below the largest applicable h^2 the group finishes as pure
+// Newtonian, otherwise it is redone with the exact piecewise polynomial.
+// ---------------------------------------------------------------------------
+template <int MODE, bool UM>
+__device__ __forceinline__ void spline_exact_f64(const double xj, const double yj, const double zj,
+                                                 const double mj_in, const double cj, const double xi,
+                                                 const double yi, const double zi, const double ci, double& ax,
+                                                 double& ay, double& az, double& sp, const double eps2) {
+    const double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    const double d  = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+    const double h2 = fmax(cj, ci);
+    const double mj = UM ? 1.0 : mj_in;
+    double w, p;
+    if (d < h2) {
+        const double r = sqrt(d), h = sqrt(h2);
+        w = spline_w_inside<double>(r, h);
+        p = -spline_phi_inside<double>(r, h);
+    } else {
+        const double ri = rsqrt_f64(d);
+        p = ri;
+        w = ri * (ri * ri);
+    }
+    if (MODE & NB_MODE_FORCE) {
+        const double f = mj * w;
+        ax = fma(f, dx, ax);
+        ay = fma(f, dy, ay);
+        az = fma(f, dz, az);
+    }
+    if (MODE & NB_MODE_POT) sp = fma(mj, p, sp);
+}
+
+template <int MODE, bool UM, int NI>
+__device__ __forceinline__ void tile_f64_spline(const unsigned char* __restrict__ stage, IState64<NI>& S,
+                                                const double eps2, const double c_max_tile) {
+    const double* __restrict__ sX = reinterpret_cast<const double*>(stage) + COMP_X * TJ;
+    const double* __restrict__ sY = reinterpret_cast<const double*>(stage) + COMP_Y * TJ;
+    const double* __restrict__ sZ = reinterpret_cast<const double*>(stage) + COMP_Z * TJ;
+    const double* __restrict__ sM = reinterpret_cast<const double*>(stage) + COMP_M * TJ;
+    const double* __restrict__ sC = reinterpret_cast<const double*>(stage) + COMP_C * TJ;
+    double h2max = c_max_tile;
+#pragma unroll
+    for (int q = 0; q < NI; ++q) h2max = fmax(h2max, S.c[q]);
+    const int hi_lim = __double2hiint(h2max);   // d may be inside only if hiword(d) <= hiword(h2max)
+
+#pragma unroll 1
+    for (int j0 = 0; j0 < TJ; j0 += 2) {
+        const double2 x2 = *reinterpret_cast<const double2*>(sX + j0);
+        const double2 y2 = *reinterpret_cast<const double2*>(sY + j0);
+        const double2 z2 = *reinterpret_cast<const double2*>(sZ + j0);
+        double2 m2 = make_double2(1.0, 1.0);
+        if (!UM) m2 = *reinterpret_cast<const double2*>(sM + j0);
+        const double xs[2] = {x2.x, x2.y}, ys[2] = {y2.x, y2.y}, zs[2] = {z2.x, z2.y}, ms[2] = {m2.x, m2.y};
+        double dx[2][NI], dy[2][NI], dz[2][NI], d[2][NI];
+        int hi_min = 0x7fffffff;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int q = 0; q < NI; ++q) {
+                dx[jj][q] = xs[jj] - S.x[q];
+                dy[jj][q] = ys[jj] - S.y[q];
+                dz[jj][q] = zs[jj] - S.z[q];
+                d[jj][q]  = fma(dx[jj][q], dx[jj][q], fma(dy[jj][q], dy[jj][q], fma(dz[jj][q], dz[jj][q], eps2)));
+                hi_min = min(hi_min, __double2hiint(d[jj][q]));
+            }
+        if (hi_min <= hi_lim) {   // rare: some pair may be inside its softening length -> exact path
+#pragma unroll 1
+            for (int jj = 0; jj < 2; ++jj) {   // re-read the j-particle from shared memory (keeps xs.. in registers)
+                const int j = j0 + jj;
+                const double xj = sX[j], yj = sY[j], zj = sZ[j], mj = sM[j], cj = sC[j];
+#pragma unroll
+                for (int q = 0; q < NI; ++q)
+                    spline_exact_f64<MODE, UM>(xj, yj, zj, mj, cj, S.x[q], S.y[q], S.z[q], S.c[q], S.ax[q], S.ay[q],
+                                               S.az[q], S.sp[q], eps2);
+            }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int q = 0; q < NI; ++q) {
+                    const double rinv = rsqrt_f64(d[jj][q]);
+                    const double mr   = UM ? rinv : ms[jj] * rinv;
+                    if (MODE & NB_MODE_POT) S.sp[q] += mr;
+                    if (MODE & NB_MODE_FORCE) {
+                        const double f = mr * (rinv * rinv);
+                        S.ax[q] = fma(f, dx[jj][q], S.ax[q]);
+                        S.ay[q] = fma(f, dy[jj][q], S.ay[q]);
+                        S.az[q] = fma(f, dz[jj][q], S.az[q]);
+                    }
+                }
+        }
+    }
+}
+
 template <int KID, int MODE, int NI, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -170,7 +268,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
         for (int q = 0; q < NI; ++q) {
             const long long ig = ig0 + static_cast<long long>(THREADS) * q;
             S.x[q] = S.y[q] = S.z[q] = 0.0;
-            S.c[q] = 1.0;
+            S.c[q] = 0.0;   // dummy i beyond the buffer: results are discarded
             if (ig < a.n_pad) {
                 const long long t = ig / TJ;
                 const int kk      = static_cast<int>(ig - t * TJ);
@@ -197,7 +295,15 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
             const double2 meta = *reinterpret_cast<const double2*>(stage + 5 * TJ * 8);   // {c_uni, m_uni} or NaN
             const bool uc = (meta.x == meta.x), um = (meta.y == meta.y);
             double m_fold = 1.0;
-            if (masked) {
+            if (KID == NB_KERNEL_SPLINE && !masked && uc) {
+                // two-phase spline needs an upper bound of the tile's h^2: available when the tile is uniform
+                if (um) {
+                    m_fold = meta.y;
+                    tile_f64_spline<MODE, true, NI>(stage, S, eps2, meta.x);
+                } else {
+                    tile_f64_spline<MODE, false, NI>(stage, S, eps2, meta.x);
+                }
+            } else if (masked) {
                 tile_f64<KID, MODE, true, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j);
             } else if (um && uc) {
                 m_fold = meta.y;
