@@ -45,8 +45,6 @@ extern "C" {
 #define NB_PREC_F32_COMP  1  /* 'float32_kahan'  : f32 pair math, per-tile f32 partials folded
                                                    into f64 running sums (compensated)          */
 #define NB_PREC_F64       2  /* 'float64'        : f64 everywhere                               */
-#define NB_PREC_F32_KAHAN 3  /* strict per-interaction Kahan (reference cuda_kernels.py:336-354);
-                                kept for accuracy comparisons, not the default                  */
 
 /* softening kernel ids (reference: fields.py:94-100) */
 #define NB_KERNEL_NEWTONIAN 0
@@ -184,7 +182,7 @@ int nb_energy(const double *vel, const void *mass, int mass_dt,
 /* ---- tuning (not part of the reference-facing surface) --------------------- */
 
 /* Select one of the compiled register-blocking variants of the plummer/spline
- * sweeps (f32: 0..4, f64: 0..2; 0 is the default; also NB_F32_VARIANT /
+ * sweeps (f32: 0..3, f64: 0..2; 0 is the default; also NB_F32_VARIANT /
  * NB_F64_VARIANT in the environment).  Changes nb_sweep_grid() results. */
 int nb_set_variant(int prec, int variant);
 int nb_get_variant(int prec);

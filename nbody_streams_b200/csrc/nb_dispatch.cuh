@@ -12,11 +12,14 @@ enum { OP_LAUNCH = 0, OP_QUERY = 1 };
 // tuning variants: (i-pairs per thread NP, min resident CTAs per SM)
 struct VariantF32 { int np, minb, ju; bool dec; };
 struct VariantF64 { int ni, minb; };
-constexpr int NV_F32 = 6;
+constexpr int NV_F32 = 4;
 constexpr int NV_F64 = 3;
 __host__ __device__ constexpr VariantF32 variant_f32(int v) {
-    return v == 1 ? VariantF32{2, 4, 4, false} : v == 2 ? VariantF32{2, 6, 4, false} : v == 3 ? VariantF32{3, 4, 4, false}
-         : v == 4 ? VariantF32{4, 3, 4, false} : v == 5 ? VariantF32{2, 5, 4, true} : VariantF32{2, 5, 4, false};
+    // 0: default (2 i-pairs/thread, 5 CTAs/SM, 4 j per iteration)   1: 4 CTAs/SM, 124 registers
+    // 2: 1 i-pair/thread, 8 CTAs/SM (best for potential-only)       3: decoupled warps (no per-tile __syncthreads)
+    // measured on B200 (profiles/r01_probe_variant_sweep.log): all within 3 % for force sweeps, 0 is best overall
+    return v == 1 ? VariantF32{2, 4, 4, false} : v == 2 ? VariantF32{1, 8, 4, false}
+         : v == 3 ? VariantF32{2, 5, 4, true} : VariantF32{2, 5, 4, false};
 }
 __host__ __device__ constexpr VariantF64 variant_f64(int v) {
     return v == 1 ? VariantF64{4, 3} : v == 2 ? VariantF64{2, 5} : VariantF64{2, 4};
@@ -58,8 +61,6 @@ inline int pick_variant_f32(int variant, int op, const SweepArgs* a, int grid, i
             case 1: return run_f32<KID, MODE, ACC, 1>(op, a, grid, out, st);
             case 2: return run_f32<KID, MODE, ACC, 2>(op, a, grid, out, st);
             case 3: return run_f32<KID, MODE, ACC, 3>(op, a, grid, out, st);
-            case 4: return run_f32<KID, MODE, ACC, 4>(op, a, grid, out, st);
-            case 5: return run_f32<KID, MODE, ACC, 5>(op, a, grid, out, st);
             default: break;
         }
     }

@@ -191,6 +191,15 @@ __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage
                     cs[4 * g] = cs[4 * g + 1] = cs[4 * g + 2] = cs[4 * g + 3] = c_tile;
                 }
             }
+        } else if (JU == 2) {   // broadcast LDS.64: two j-particles per load
+            const float2 x2 = *reinterpret_cast<const float2*>(sX + j0);
+            const float2 y2 = *reinterpret_cast<const float2*>(sY + j0);
+            const float2 z2 = *reinterpret_cast<const float2*>(sZ + j0);
+            xs[0] = x2.x; xs[1] = x2.y; ys[0] = y2.x; ys[1] = y2.y; zs[0] = z2.x; zs[1] = z2.y;
+            ms[0] = ms[1] = 1.f;
+            cs[0] = cs[1] = c_tile;
+            if (!UM) { const float2 m2 = *reinterpret_cast<const float2*>(sM + j0); ms[0] = m2.x; ms[1] = m2.y; }
+            if (kNeedC) { const float2 c2 = *reinterpret_cast<const float2*>(sC + j0); cs[0] = c2.x; cs[1] = c2.y; }
         } else {
             xs[0] = sX[j0]; ys[0] = sY[j0]; zs[0] = sZ[j0]; ms[0] = sM[j0]; cs[0] = sC[j0];
         }

@@ -330,6 +330,35 @@ class DirectEngine:
                                         self.n_local, 0.5 * dt, self._stream()))
         self.launches += 1
 
+    def capture_step(self, mode: int, dt: float):
+        """Capture one KDK step (kick+drift+repack, sweep, finish, kick) into a CUDA graph and return a
+        callable that replays it: one graph launch per step instead of four kernel launches through
+        Python/ctypes — what matters for N <~ 1e5 where a step is shorter than its launch overhead.
+        Single rank, no hooks (their accelerations change every step)."""
+        assert self.world == 1
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            self._grid(mode)
+            self._workspace(self._grid(mode))          # allocate outside the capture
+            graph = torch.cuda.CUDAGraph()
+            saved_events, self.sweep_events = self.sweep_events, None
+            with torch.cuda.graph(graph, stream=side):
+                self.kick_drift(dt)
+                self.compute(mode)
+                self.kick(dt)
+            self.sweep_events = saved_events
+        per_step = 4
+
+        def replay():
+            graph.replay()
+            self.launches += per_step
+
+        self.launches -= per_step      # the capture pass recorded the launches without running them
+        replay.graph = graph
+        return replay
+
     def energy(self, with_phi: bool = True, with_acc: bool = False) -> np.ndarray:
         """[KE, PE, px, py, pz, fx, fy, fz] summed over all ranks (float64, host)."""
         torch = self.torch

@@ -148,6 +148,7 @@ def run_nbody_gpu(
     overlap: bool = True,
     diagnostics: list | None = None,
     diagnostics_every: int = 0,
+    cuda_graph: bool | None = None,
 ) -> np.ndarray:
     """GPU direct-summation N-body run with the KDK leapfrog of the reference.
 
@@ -167,7 +168,9 @@ def run_nbody_gpu(
     its ranks), ``overlap`` (sweep the local shard while the all-gather is in
     flight; False = global summation order), ``diagnostics`` (list that
     receives ``(step, time, KE, PE, px, py, pz)`` every ``diagnostics_every``
-    steps, from the fused sweep).
+    steps, from the fused sweep), ``cuda_graph`` (replay the whole step as one
+    CUDA graph; default: on for a single rank without hooks and N <= 131072,
+    where launch overhead would otherwise dominate the step).
     """
     torch = _lib.require_cuda()   # ImportError when there is no CUDA device / library (reference: "CuPy required")
 
@@ -339,17 +342,26 @@ def run_nbody_gpu(
     t_start = pytime.perf_counter()
     _report_every = max(1, remaining_steps // 20)
 
+    if cuda_graph is None:
+        cuda_graph = world == 1 and not hooks and N <= 131072
+    graph_step = eng.capture_step(mode, dt) if (cuda_graph and world == 1 and not hooks and remaining_steps > 0
+                                                 and eng.n_local > 0) else None
+
     for step_i in range(1, remaining_steps + 1):
         current_step = start_step + step_i
 
-        eng.kick_drift(dt, acc_ext)          # half kick + drift (+ repack own shard), fused
-        time += dt
-        eng.compute(mode)                    # all-gather (world>1) + sweep + finish
-        if hooks:
-            acc_ext = extra_acc(current_step, time)
-            if force_extra is not None:
-                acc_ext = add_force_extra(acc_ext, time)
-        eng.kick(dt, acc_ext)                # half kick
+        if graph_step is not None:
+            graph_step()                     # the same four launches, replayed as one CUDA graph
+            time += dt
+        else:
+            eng.kick_drift(dt, acc_ext)          # half kick + drift (+ repack own shard), fused
+            time += dt
+            eng.compute(mode)                    # all-gather (world>1) + sweep + finish
+            if hooks:
+                acc_ext = extra_acc(current_step, time)
+                if force_extra is not None:
+                    acc_ext = add_force_extra(acc_ext, time)
+            eng.kick(dt, acc_ext)                # half kick
 
         while snapshot_counter < len(snapshot_steps) and current_step >= snapshot_steps[snapshot_counter]:
             if save_snapshots:

@@ -287,7 +287,7 @@ def test_results_independent_of_tuning_variant(nb):
     ref = oracle.compute_nbody_forces_cpu(xv[:, :3], m, 0.05, kernel="plummer")
     try:
         pref = oracle.compute_nbody_potential_cpu(xv[:, :3], m, 0.05, kernel="plummer")
-        for v in range(6):
+        for v in range(4):
             lib.nb_set_variant(0, v)
             for kern, r_a, r_p in (("plummer", ref, pref),):
                 acc, phi = nb.compute_nbody_forces_potential_gpu(xv[:, :3], m, 0.05, precision="float32_kahan",

@@ -158,3 +158,21 @@ def test_run_error_paths(nb, tmp_path):
     (tmp_path / "snapshot.h5").write_bytes(b"x")
     with pytest.raises(FileExistsError):
         nb.run_nbody_gpu(xv, m, 0, 1e-3, 1e-4, 0.01, output_dir=str(tmp_path), save_snapshots=True, verbose=False)
+
+
+def test_cuda_graph_step_is_bitwise_identical(nb, tmp_path):
+    xv, m = nb.make_plummer_sphere(3000, M_total=1e9, a=1.0, seed=21)
+    kw = dict(kernel="spline", save_snapshots=False, verbose=False)
+    for precision in ("float32_kahan", "float64"):
+        a = nb.run_nbody_gpu(xv, m, 0.0, 25e-4, 1e-4, 0.05, precision=precision, cuda_graph=True,
+                             output_dir=str(tmp_path / f"g{precision}"), **kw)
+        b = nb.run_nbody_gpu(xv, m, 0.0, 25e-4, 1e-4, 0.05, precision=precision, cuda_graph=False,
+                             output_dir=str(tmp_path / f"n{precision}"), **kw)
+        assert np.array_equal(a, b)
+    # with diagnostics (fused potential inside the graph)
+    d1, d2 = [], []
+    nb.run_nbody_gpu(xv, m, 0.0, 10e-4, 1e-4, 0.05, cuda_graph=True, diagnostics=d1, diagnostics_every=5,
+                     output_dir=str(tmp_path / "d1"), **kw)
+    nb.run_nbody_gpu(xv, m, 0.0, 10e-4, 1e-4, 0.05, cuda_graph=False, diagnostics=d2, diagnostics_every=5,
+                     output_dir=str(tmp_path / "d2"), **kw)
+    assert d1 == d2 and len(d1) == 3
