@@ -82,7 +82,8 @@ __device__ __forceinline__ void pair_f32(const float xj, const float yj, const f
     if (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2) {
         const f2 mr    = UM ? rinv : mul2(mj, rinv);
         const f2 rinv2 = mul2(rinv, rinv);
-        const f2 t     = mul2(h2, rinv2);
+        // the packed c holds h^2 + eps2 (it seeds the r^2 chain); the correction terms want the bare h^2
+        const f2 t     = mul2(add2(h2, splat(-eps2)), rinv2);
         if (MODE & NB_MODE_POT) {
             f2 pf;
             if (KID == NB_KERNEL_DEHNEN_K1) pf = fma2(splat(0.5f), t, splat(1.f));

@@ -45,7 +45,7 @@ __device__ __forceinline__ void pair_f64(const double xj, const double yj, const
     const double mr   = (UM && !MASK) ? rinv : mj * rinv;
     if (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2) {
         const double rinv2 = rinv * rinv;
-        const double t     = h2 * rinv2;
+        const double t     = (h2 - eps2) * rinv2;   // c = h^2 + eps2 seeds the r^2 chain; the terms use bare h^2
         if (MODE & NB_MODE_POT) {
             const double pf = (KID == NB_KERNEL_DEHNEN_K1) ? fma(0.5, t, 1.0) : fma(t, fma(0.375, t, 0.5), 1.0);
             sp = fma(mr, pf, sp);

@@ -9,7 +9,7 @@ import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import nbody_streams_b200 as nb  # noqa: E402
-import oracle  # noqa: E402  (tools/ is measurement infrastructure, not product code)
+import oracle  # noqa: E402  (lives under tests/: the oracle is only the checker here)
 
 
 def rel_rms(a, r):
