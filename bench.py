@@ -296,6 +296,31 @@ def main():
                "ms_per_call": dt_e2e / n_e2e * 1e3, "calls": n_e2e,
                "api": "compute_nbody_forces_potential_gpu(numpy pos, scalar mass, scalar softening) -> numpy"}
 
+    # ---- context: the other sweeps of this workload on the same resident state (1 GPU, device-timed) ----
+    sweeps = None
+    if world == 1 and not args.skip_e2e:
+        from nbody_streams_b200._lib import MODE_FORCE
+
+        sweeps = {}
+        for kname, mode, mname in (("plummer", MODE_FORCE, "force"), ("spline", MODE_FORCE, "force"),
+                                   ("spline", MODE_BOTH, "force+potential")):
+            e = DirectEngine(N, float(m[0]), args.softening, prec, KERNEL_MAP[kname], nb.G_DEFAULT,
+                             EPS2_DEFAULT[args.precision], device)
+            e.packed = eng.packed if kname == args.kernel else e.packed
+            if kname != args.kernel:
+                e.load_state(xv)
+            e.compute(mode, positions_changed=False)          # warm-up
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(2):
+                e.compute(mode, positions_changed=False)
+            a1.record()
+            torch.cuda.synchronize()
+            ms = a0.elapsed_time(a1) / 2
+            sweeps[f"{kname}_{mname}"] = {"ms": ms, "interactions_per_s": float(N) * N / (ms * 1e-3),
+                                          "frac_of_measured_fp32_peak": float(N) * N / (ms * 1e-3) * 20 / 1e12 / peak_tf}
+            del e
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_sample(args, xv, m, args.cpu_seconds)
@@ -319,6 +344,7 @@ def main():
             },
             "fraction_of_fp32_peak": value * FLOPS_PER_INTERACTION / 1e12 / (peak_tf * world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
+            "other_sweeps": sweeps,
             "clocks": clocks,
         }
         print_json(line)
