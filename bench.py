@@ -306,9 +306,7 @@ def main():
                                    ("spline", MODE_BOTH, "force+potential")):
             e = DirectEngine(N, float(m[0]), args.softening, prec, KERNEL_MAP[kname], nb.G_DEFAULT,
                              EPS2_DEFAULT[args.precision], device)
-            e.packed = eng.packed if kname == args.kernel else e.packed
-            if kname != args.kernel:
-                e.load_state(xv)
+            e.load_state(xv)
             e.compute(mode, positions_changed=False)          # warm-up
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
