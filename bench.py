@@ -56,6 +56,8 @@ def parse():
     p.add_argument("--softening", type=float, default=0.01)
     p.add_argument("--dt", type=float, default=1e-4)
     p.add_argument("--no-overlap", action="store_true", help="global summation order (deterministic) at N>1")
+    p.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                   help="N>1: NCCL all-gather of the j-records, or the exchange fused into the drift kernel (NVLink stores)")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -208,7 +210,7 @@ def main():
     peak_tf = 2.0 * ops.value / 1e12
 
     eng = DirectEngine(N, float(m[0]), args.softening, prec, kid, nb.G_DEFAULT, EPS2_DEFAULT[args.precision], device,
-                       overlap=not args.no_overlap)
+                       overlap=not args.no_overlap, exchange=args.exchange)
     eng.load_state(xv)
     eng.compute(MODE_BOTH, positions_changed=False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
@@ -335,7 +337,9 @@ def main():
                             f"softening={args.softening} (BASELINE config 3)",
                 "step": "KDK leapfrog step: fused kick+drift+repack, all-gather (N>1), one force+potential sweep "
                         "over N^2 pairs, fix-up, half kick; float64 pos/vel resident on the device",
-                "parallelism": f"i-particles sharded over {world} GPU(s), j-records all-gathered over NCCL"
+                "parallelism": f"i-particles sharded over {world} GPU(s), j-records "
+                               + ("pushed to all ranks by the fused kick+drift kernel over NVLink peer memory"
+                                  if (world > 1 and args.exchange == "p2p") else "all-gathered over NCCL")
                                + (", local-shard sweep overlapped with the gather" if world > 1 and not args.no_overlap else ""),
                 "l2": "256 MiB memset between steps (inside the timed region)",
                 "tuning_variant": int(lib.nb_get_variant(prec)),

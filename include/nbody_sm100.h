@@ -166,6 +166,18 @@ int nb_kick_drift_pack(int prec, double *pos, double *vel,
                        void *packed, long first, long n,
                        double dt_half, double dt, void *stream);
 
+/* Multi-GPU variant of nb_kick_drift_pack that fuses the exchange: the refreshed x,y,z are stored
+ * straight into the packed buffer of every rank over NVLink — through `mc_packed`, the NVSwitch
+ * multicast address of the (symmetric) packed buffers (one multimem.st per value, replicated by the
+ * switch), or, when mc_packed is NULL, through the n_peers (<= 8) mapped peer pointers in the HOST
+ * array peer_packed (which includes this rank's own buffer).  Replaces kick_drift_pack + all-gather.
+ * The caller must order steps across ranks (barrier before: peers are done reading the old records;
+ * barrier after: every rank's stores have landed). */
+int nb_kick_drift_push(int prec, double *pos, double *vel,
+                       const void *acc, int acc_dt, const double *acc_ext,
+                       void *const *peer_packed, int n_peers, void *mc_packed,
+                       long first, long n, double dt_half, double dt, void *stream);
+
 /* vel += (acc [+ acc_ext]) * dt_half */
 int nb_kick(double *vel, const void *acc, int acc_dt, const double *acc_ext,
             long n, double dt_half, void *stream);

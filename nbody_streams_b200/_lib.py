@@ -45,6 +45,7 @@ SIGNATURES = {
     "nb_direct": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _d, _vp, _i, _d, _l, _d, _d, _vp, _vp, _sz, _i, _vp, _vp,
                        _vp]),
     "nb_kick_drift_pack": (_i, [_i, _vp, _vp, _vp, _i, _vp, _vp, _l, _l, _d, _d, _vp]),
+    "nb_kick_drift_push": (_i, [_i, _vp, _vp, _vp, _i, _vp, C.POINTER(_vp), _i, _vp, _l, _l, _d, _d, _vp]),
     "nb_kick": (_i, [_vp, _vp, _i, _vp, _l, _d, _vp]),
     "nb_energy_workspace_bytes": (_sz, [_l]),
     "nb_energy": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _l, _vp, _vp, _vp]),

@@ -16,6 +16,9 @@ int nb_launch_kick_drift_pack(int prec, double* pos, double* vel, const void* ac
                               double dt, cudaStream_t st);
 int nb_launch_kick(double* vel, const void* acc, int acc_dt, const double* acc_ext, long long n, double dt_half,
                    cudaStream_t st);
+int nb_launch_kick_drift_push(int prec, double* pos, double* vel, const void* acc, int acc_dt,
+                              const double* acc_ext, void* const* peer_packed, int n_peers, void* mc_packed,
+                              long long first, long long n, double dt_half, double dt, cudaStream_t st);
 size_t nb_energy_ws_bytes(long long n);
 int nb_launch_energy(const double* vel, const void* mass, int mass_dt, const void* phi, int phi_dt,
                      const void* acc, int acc_dt, long long n, double* partials, double* out, cudaStream_t st);
@@ -278,6 +281,15 @@ int nb_kick_drift_pack(int prec, double* pos, double* vel, const void* acc, int 
     if (!valid_prec(prec) || !pos || !vel || !acc || n < 0 || first < 0) return NB_E_INVALID_ARG;
     return nb_launch_kick_drift_pack(prec, pos, vel, acc, acc_dt, acc_ext, packed, first, n, dt_half, dt,
                                      static_cast<cudaStream_t>(stream));
+}
+
+int nb_kick_drift_push(int prec, double* pos, double* vel, const void* acc, int acc_dt, const double* acc_ext,
+                       void* const* peer_packed, int n_peers, void* mc_packed, long first, long n, double dt_half,
+                       double dt, void* stream) {
+    if (!valid_prec(prec) || !pos || !vel || !acc || n < 0 || first < 0) return NB_E_INVALID_ARG;
+    if (!mc_packed && (!peer_packed || n_peers < 1 || n_peers > 8)) return NB_E_INVALID_ARG;
+    return nb_launch_kick_drift_push(prec, pos, vel, acc, acc_dt, acc_ext, peer_packed, n_peers, mc_packed, first, n,
+                                     dt_half, dt, static_cast<cudaStream_t>(stream));
 }
 
 int nb_kick(double* vel, const void* acc, int acc_dt, const double* acc_ext, long n, double dt_half,

@@ -167,6 +167,64 @@ __global__ void kick_drift_pack_kernel(double* __restrict__ pos, double* __restr
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fused kick + drift + repack + EXCHANGE over NVLink peer memory (multi-GPU, exchange='p2p'):
+// the new x,y,z of this rank's particles are stored straight into the packed buffer of EVERY rank —
+// either one multimem.st per value to the NVSwitch multicast address (the switch replicates it to all
+// GPUs) or one plain store per peer through its mapped peer pointer — so no separate all-gather runs.
+// The caller brackets steps with symmetric-memory barriers (see engine.py).
+// ---------------------------------------------------------------------------
+struct PeerPtrs {
+    unsigned char* p[8];
+    int count;
+};
+
+__device__ __forceinline__ void multimem_st(float* addr, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st(double* addr, double v) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+template <typename AT, typename T>
+__global__ void kick_drift_push_kernel(double* __restrict__ pos, double* __restrict__ vel,
+                                       const AT* __restrict__ acc, const double* __restrict__ acc_ext,
+                                       const PeerPtrs peers, unsigned char* __restrict__ mc, long long first,
+                                       long long n, double dt_half, double dt) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double a = static_cast<double>(acc[3 * i + d]);
+        if (acc_ext) a += acc_ext[3 * i + d];
+        const double v = vel[3 * i + d] + a * dt_half;
+        vel[3 * i + d] = v;
+        p[d] = pos[3 * i + d] + v * dt;
+        pos[3 * i + d] = p[d];
+    }
+    constexpr int TB = (sizeof(T) == 8) ? TILE_BYTES_F64 : TILE_BYTES_F32;
+    const long long g = first + i;
+    const long long t = g / TJ;
+    const int k       = static_cast<int>(g - t * TJ);
+    const size_t off  = static_cast<size_t>(t) * TB;
+    if (mc) {
+        T* tb = reinterpret_cast<T*>(mc + off);
+        multimem_st(tb + COMP_X * TJ + k, static_cast<T>(p[0]));
+        multimem_st(tb + COMP_Y * TJ + k, static_cast<T>(p[1]));
+        multimem_st(tb + COMP_Z * TJ + k, static_cast<T>(p[2]));
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r >= peers.count) break;
+            T* tb = reinterpret_cast<T*>(peers.p[r] + off);
+            tb[COMP_X * TJ + k] = static_cast<T>(p[0]);
+            tb[COMP_Y * TJ + k] = static_cast<T>(p[1]);
+            tb[COMP_Z * TJ + k] = static_cast<T>(p[2]);
+        }
+    }
+}
+
 template <typename AT>
 __global__ void kick_kernel(double* __restrict__ vel, const AT* __restrict__ acc,
                             const double* __restrict__ acc_ext, long long n3, double dt_half) {
@@ -312,6 +370,33 @@ int nb_launch_kick_drift_pack(int prec, double* pos, double* vel, const void* ac
             kick_drift_pack_kernel<float, float><<<blocks, threads, 0, st>>>(
                 pos, vel, static_cast<const float*>(acc), acc_ext, tiles, first, n, dt_half, dt);
     }
+    NB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int nb_launch_kick_drift_push(int prec, double* pos, double* vel, const void* acc, int acc_dt,
+                              const double* acc_ext, void* const* peer_packed, int n_peers, void* mc_packed,
+                              long long first, long long n, double dt_half, double dt, cudaStream_t st) {
+    if (n <= 0) return 0;
+    PeerPtrs pp;
+    pp.count = n_peers;
+    for (int r = 0; r < 8; ++r) pp.p[r] = r < n_peers ? static_cast<unsigned char*>(peer_packed[r]) : nullptr;
+    unsigned char* mc = static_cast<unsigned char*>(mc_packed);
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((n + threads - 1) / threads);
+    const bool f64 = (prec == NB_PREC_F64), a64 = (acc_dt == NB_DT_F64);
+    if (f64 && a64)
+        kick_drift_push_kernel<double, double><<<blocks, threads, 0, st>>>(pos, vel, static_cast<const double*>(acc),
+                                                                           acc_ext, pp, mc, first, n, dt_half, dt);
+    else if (f64)
+        kick_drift_push_kernel<float, double><<<blocks, threads, 0, st>>>(pos, vel, static_cast<const float*>(acc),
+                                                                          acc_ext, pp, mc, first, n, dt_half, dt);
+    else if (a64)
+        kick_drift_push_kernel<double, float><<<blocks, threads, 0, st>>>(pos, vel, static_cast<const double*>(acc),
+                                                                          acc_ext, pp, mc, first, n, dt_half, dt);
+    else
+        kick_drift_push_kernel<float, float><<<blocks, threads, 0, st>>>(pos, vel, static_cast<const float*>(acc),
+                                                                         acc_ext, pp, mc, first, n, dt_half, dt);
     NB_CUDA_OK(cudaGetLastError());
     return 0;
 }

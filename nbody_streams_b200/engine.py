@@ -130,13 +130,19 @@ class DirectEngine:
     prec : library precision code; kernel_id : 0..4; G, eps2 : floats.
     device : torch CUDA device of this rank.
     group : torch.distributed process group (None = default group / single process).
+    exchange : "nccl" (default) — in-place NCCL all-gather of the packed shards each step;
+               "p2p" — the packed buffer lives in torch symmetric memory and the fused
+               kick+drift kernel stores the refreshed records straight into every rank's buffer over
+               NVLink (NVSwitch multicast when available, else one store per peer), bracketed by
+               symmetric-memory barriers: no separate collective runs.
     overlap : sweep the local j-shard while the all-gather is in flight (default);
               False sweeps all tiles in global (j-ascending) order after the gather.
               Either way results are bitwise reproducible for a given rank count and agree
               with the 1-GPU result to rounding (the stream-K pieces are cut at other tiles).
     """
 
-    def __init__(self, N, mass, softening, prec, kernel_id, G, eps2, device, group=None, overlap=True):
+    def __init__(self, N, mass, softening, prec, kernel_id, G, eps2, device, group=None, overlap=True,
+                 exchange="nccl"):
         torch = _lib.require_cuda()
         self.torch = torch
         self.lib = _lib.load()
@@ -154,8 +160,23 @@ class DirectEngine:
         self.dtype = torch.float64 if prec == PREC_F64 else torch.float32
         self.acc_dt = DT_F64 if prec == PREC_F64 else DT_F32
 
+        self.exchange = exchange if self.world > 1 else "nccl"
+        if self.exchange not in ("nccl", "p2p"):
+            raise ValueError(f"exchange must be 'nccl' or 'p2p', got {exchange!r}")
+        self._symm = None
         with torch.cuda.device(self.device):
-            self.packed = torch.zeros(self.shard_bytes * self.world, dtype=torch.uint8, device=self.device)
+            if self.exchange == "p2p":
+                import torch.distributed._symmetric_memory as symm_mem
+
+                self.packed = symm_mem.empty(self.shard_bytes * self.world, dtype=torch.uint8, device=self.device)
+                self.packed.zero_()
+                self._symm = symm_mem.rendezvous(self.packed, group if group is not None else _dist().group.WORLD)
+                ptrs = [int(p) for p in self._symm.buffer_ptrs]
+                self._peer_ptrs = (C.c_void_p * self.world)(*ptrs)
+                self._mc_ptr = int(getattr(self._symm, "multicast_ptr", 0) or 0)
+                self.overlap = True     # the local sweep always runs between the push and its barrier
+            else:
+                self.packed = torch.zeros(self.shard_bytes * self.world, dtype=torch.uint8, device=self.device)
             self._grids = {}
             self._ws = None
             self._ws_bytes = 0
@@ -280,7 +301,8 @@ class DirectEngine:
         n_jt = (C.c_int * 4)(0, 0, 0, 0)
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
-            if self.world > 1 and positions_changed:
+            p2p = self.exchange == "p2p"
+            if self.world > 1 and positions_changed and not p2p:
                 self.comm_stream.wait_stream(cur)          # shard records are written on `cur`
                 with torch.cuda.stream(self.comm_stream):
                     allgather_shards(self.packed, self.layout, self.rank, self.shard_bytes, self.group)
@@ -289,7 +311,11 @@ class DirectEngine:
                     # slot 0: own shard (no dependency on the collective)
                     self._sweep(mode, t0, t1, 0, 0, ws, 0, grid)
                     n_jt[0] = t1 - t0
-                    cur.wait_stream(self.comm_stream)
+                    if p2p:
+                        if positions_changed:
+                            self._symm.barrier(channel=1)   # every rank's pushed records have landed
+                    else:
+                        cur.wait_stream(self.comm_stream)
                     # slot 1: every other rank's tiles, as two ranges around mine
                     self._sweep(mode, 0, t0, t1, n_tiles, ws, 1, grid)
                     n_jt[1] = n_tiles - (t1 - t0)
@@ -306,11 +332,26 @@ class DirectEngine:
                                          self.phi.data_ptr() if mode & MODE_POT else None, self._stream()))
                 self.launches += 1
             elif self.world > 1:
-                cur.wait_stream(self.comm_stream)
+                if p2p:
+                    if positions_changed:
+                        self._symm.barrier(channel=1)
+                else:
+                    cur.wait_stream(self.comm_stream)
 
     # -- KDK pieces -----------------------------------------------------------
     def kick_drift(self, dt: float, acc_ext=None) -> None:
         """vel += acc*dt/2 ; pos += vel*dt ; refresh own packed x,y,z (one fused kernel)."""
+        if self.exchange == "p2p":
+            with self.torch.cuda.device(self.device):
+                self._symm.barrier(channel=0)       # every rank is done reading the previous records
+                if self.n_local > 0:
+                    _lib.check(self.lib.nb_kick_drift_push(
+                        self.prec, self.pos.data_ptr(), self.vel.data_ptr(), self.acc.data_ptr(), self.acc_dt,
+                        acc_ext.data_ptr() if acc_ext is not None else None,
+                        self._peer_ptrs, self.world, self._mc_ptr if self._mc_ptr else None,
+                        self.first, self.n_local, 0.5 * dt, dt, self._stream()))
+                    self.launches += 1
+            return
         if self.n_local == 0:
             return
         with self.torch.cuda.device(self.device):

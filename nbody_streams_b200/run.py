@@ -149,6 +149,7 @@ def run_nbody_gpu(
     diagnostics: list | None = None,
     diagnostics_every: int = 0,
     cuda_graph: bool | None = None,
+    exchange: str = "nccl",
 ) -> np.ndarray:
     """GPU direct-summation N-body run with the KDK leapfrog of the reference.
 
@@ -170,7 +171,9 @@ def run_nbody_gpu(
     receives ``(step, time, KE, PE, px, py, pz)`` every ``diagnostics_every``
     steps, from the fused sweep), ``cuda_graph`` (replay the whole step as one
     CUDA graph; default: on for a single rank without hooks and N <= 131072,
-    where launch overhead would otherwise dominate the step).
+    where launch overhead would otherwise dominate the step), ``exchange`` (multi-GPU only:
+    ``"nccl"`` all-gathers the packed j-records each step, ``"p2p"`` fuses the exchange into the
+    kick+drift kernel, which stores the refreshed records into every rank's buffer over NVLink).
     """
     torch = _lib.require_cuda()   # ImportError when there is no CUDA device / library (reference: "CuPy required")
 
@@ -272,7 +275,7 @@ def run_nbody_gpu(
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     eng = DirectEngine(N, masses, softening, prec, KERNEL_MAP[kernel.lower()], G, EPS2_DEFAULT[prec_key], device,
-                       group=group, overlap=overlap)
+                       group=group, overlap=overlap, exchange=exchange)
     eng.load_state(xv)
 
     want_phi = bool(debug_energy or diagnostics is not None)

@@ -58,6 +58,15 @@ def main():
     dist.barrier()
     ok &= (out / "det" / "restart.npz").exists()
 
+    # exchange fused into the drift kernel: NVLink peer stores / NVSwitch multicast through torch symmetric memory
+    if "--p2p" in sys.argv:
+        p2p = nb.run_nbody_gpu(xv, mass, 0.0, steps * dt, dt, h, output_dir=str(out / "p2p"), exchange="p2p", **kw)
+        e_p2p = np.abs(p2p - ref).max() / np.abs(ref).max()
+        eng = nb.run_nbody_gpu.last_engine
+        msgs.append(f"run float64 exchange=p2p vs 1 GPU: {e_p2p:.2e} (bitwise equal to NCCL overlap run: "
+                    f"{np.array_equal(p2p, ovl)}; multicast {'yes' if eng._mc_ptr else 'no'})")
+        ok &= bool(e_p2p < 1e-12) and bool(np.array_equal(p2p, ovl))
+
     kw32 = dict(kw, precision="float32_kahan")
     diags = []
     f32 = nb.run_nbody_gpu(xv, mass, 0.0, steps * dt, dt, h, output_dir=str(out / "f32"), diagnostics=diags,

@@ -18,7 +18,7 @@ def test_sharded_run_matches_single_gpu(tmp_path):
     world = 2 if n < 4 else 4
     worker = Path(__file__).resolve().parent / "mgpu_worker.py"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29533", str(worker), str(tmp_path)]
+           "--master-addr", "127.0.0.1", "--master-port", "29533", str(worker), str(tmp_path), "--p2p"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=550)
     res = (tmp_path / "result.txt").read_text() if (tmp_path / "result.txt").exists() else ""
     assert r.returncode == 0 and res.startswith("OK"), f"{res}\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}"
