@@ -176,3 +176,62 @@ def test_cuda_graph_step_is_bitwise_identical(nb, tmp_path):
     nb.run_nbody_gpu(xv, m, 0.0, 10e-4, 1e-4, 0.05, cuda_graph=False, diagnostics=d2, diagnostics_every=5,
                      output_dir=str(tmp_path / "d2"), **kw)
     assert d1 == d2 and len(d1) == 3
+
+
+def test_debug_energy_prints_virial_and_drift(nb, tmp_path, capsys):
+    # reference tests/test_multi_species.py:714-760: debug_energy=True prints "[Energy t=0]" and "Q=... dE/E=..."
+    xv, m = nb.make_plummer_sphere(400, M_total=1e8, a=1.0, seed=2)
+    nb.run_nbody_gpu(xv, m, 0.0, 40e-4, 1e-4, 0.05, output_dir=str(tmp_path), save_snapshots=False, verbose=True,
+                     debug_energy=True)
+    out = capsys.readouterr().out
+    assert "GPU N-body Integration" in out and "[Energy t=0]" in out
+    assert "Q=" in out and "dE/E=" in out and "Integration Complete" in out
+
+
+def test_old_api_without_species_and_scalar_softening(nb, tmp_path):
+    # reference tests/test_multi_species.py:659-707: run_nbody_gpu(phase_space, masses, t0, t1, dt, softening)
+    xv, m = nb.make_plummer_sphere(300, M_total=1e8, a=1.0, seed=4)
+    final = nb.run_nbody_gpu(xv, m, 0.0, 5e-4, 1e-4, 0.05, output_dir=str(tmp_path), save_snapshots=False,
+                             verbose=False)
+    assert final.shape == (300, 6) and np.isfinite(final).all()
+    r = np.load(tmp_path / "restart.npz")
+    assert "mass_arr" not in r.files            # legacy restart layout without species keys
+    # per-particle softening array and float32 masses are accepted as in the reference
+    final2 = nb.run_nbody_gpu(xv, m.astype(np.float32), 0.0, 5e-4, 1e-4, np.full(300, 0.05), precision="float32",
+                              output_dir=str(tmp_path / "b"), save_snapshots=False, verbose=False)
+    assert np.allclose(final2, final, rtol=1e-4, atol=1e-6 * np.abs(final).max())
+
+
+def test_run_simulation_species_counts(nb, tmp_path):
+    # reference tests/test_multi_species.py:501-604: 1, 2 and 3 species incl. a single heavy particle
+    xv1, m1 = nb.make_plummer_sphere(200, M_total=1e8, a=1.0, seed=1)
+    xv2, m2 = nb.make_plummer_sphere(100, M_total=1e6, a=0.3, seed=2)
+    cases = [
+        (xv1, [nb.Species.dark(200, float(m1[0]), 0.05)]),
+        (np.vstack([xv1, xv2]), [nb.Species.dark(200, float(m1[0]), 0.05), nb.Species.star(100, m2, 0.02)]),
+        (np.vstack([xv1, xv2, np.zeros((1, 6))]),
+         [nb.Species.dark(200, float(m1[0]), 0.05), nb.Species.star(100, float(m2[0]), np.full(100, 0.02)),
+          nb.Species("bh", 1, 1e6, 0.01)]),
+    ]
+    for i, (xv, sp) in enumerate(cases):
+        res = nb.run_simulation(xv, sp, 0.0, 3e-4, 1e-4, output_dir=str(tmp_path / str(i)), save_snapshots=False,
+                                verbose=False)
+        assert list(res) == [s.name for s in sp]
+        for s in sp:
+            assert res[s.name].shape == (s.N, 6) and res[s.name].dtype == np.float64
+        r = np.load(tmp_path / str(i) / "restart.npz")
+        assert [n.decode() for n in r["species_names"]] == [s.name for s in sp]
+        assert list(r["species_N"]) == [s.N for s in sp] and int(r["step"]) == 3
+
+
+def test_snapshot_files_when_h5py_is_available(nb, tmp_path):
+    h5py = pytest.importorskip("h5py")
+    xv, m = nb.make_plummer_sphere(128, M_total=1e8, a=1.0, seed=9)
+    final = nb.run_simulation(xv, [nb.Species.dark(128, float(m[0]), 0.05)], 0.0, 10e-4, 1e-4,
+                              output_dir=str(tmp_path), save_snapshots=True, snapshots=3, verbose=False)["dark"]
+    with h5py.File(tmp_path / "snapshot.h5") as f:
+        assert sorted(f["snapshots"]) == ["snap.000", "snap.001", "snap.002"]
+        assert np.array_equal(f["snapshots/snap.002"][...], final)      # final array == last snapshot
+        assert int(f["properties/dark/N"][()]) == 128
+    t = np.loadtxt(tmp_path / "snapshot.times", comments="#")
+    assert np.allclose(t[:, 1], [0.0, 5e-4, 10e-4])
