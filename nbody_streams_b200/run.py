@@ -306,10 +306,34 @@ def run_nbody_gpu(
         fe = torch.as_tensor(fe, device=eng.device).to(torch.float64)[eng.layout.rows(eng.rank)]
         return fe.contiguous() if total is None else (total + fe).contiguous()
 
+    # Hooks run on their own stream (single rank): positions are final once the drift kernel has run, so the
+    # device->host copy for a host potential, the CPU evaluation (agama-like: 10-20 ms in the reference's own
+    # docs) and the host->device copy of the result all overlap the O(N^2) sweep queued on the main stream.
+    # The reference serialises them (run.py:197-212, :689-692).
+    hook_stream = torch.cuda.Stream(eng.device) if hooks else None
+    ev_drift = torch.cuda.Event() if hooks else None
+
+    def eval_hooks(step, t, with_force_extra):
+        cur = torch.cuda.current_stream(eng.device)
+        if world > 1:
+            total = extra_acc(step, t)
+            return add_force_extra(total, t) if with_force_extra else total
+        hook_stream.wait_event(ev_drift)
+        with torch.cuda.stream(hook_stream):
+            total = extra_acc(step, t)
+            if with_force_extra:
+                total = add_force_extra(total, t)
+        cur.wait_stream(hook_stream)
+        if total is not None:
+            total.record_stream(cur)
+        return total
+
     if verbose:
         print("Computing initial forces...")
+    if hooks:
+        ev_drift.record(torch.cuda.current_stream(eng.device))
     eng.compute(mode, positions_changed=False)
-    acc_ext = extra_acc(start_step, time) if hooks else None
+    acc_ext = eval_hooks(start_step, time, False) if hooks else None
     # the reference applies force_extra only inside the loop (run.py:689-692), not to the initial acceleration
 
     E_ref = 0.0
@@ -358,12 +382,12 @@ def run_nbody_gpu(
             time += dt
         else:
             eng.kick_drift(dt, acc_ext)          # half kick + drift (+ repack own shard), fused
-            time += dt
-            eng.compute(mode)                    # all-gather (world>1) + sweep + finish
             if hooks:
-                acc_ext = extra_acc(current_step, time)
-                if force_extra is not None:
-                    acc_ext = add_force_extra(acc_ext, time)
+                ev_drift.record(torch.cuda.current_stream(eng.device))
+            time += dt
+            eng.compute(mode)                    # all-gather (world>1) + sweep + finish (asynchronous)
+            if hooks:                            # evaluated while the sweep runs
+                acc_ext = eval_hooks(current_step, time, force_extra is not None)
             eng.kick(dt, acc_ext)                # half kick
 
         while snapshot_counter < len(snapshot_steps) and current_step >= snapshot_steps[snapshot_counter]:

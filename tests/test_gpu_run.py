@@ -235,3 +235,36 @@ def test_snapshot_files_when_h5py_is_available(nb, tmp_path):
         assert int(f["properties/dark/N"][()]) == 128
     t = np.loadtxt(tmp_path / "snapshot.times", comments="#")
     assert np.allclose(t[:, 1], [0.0, 5e-4, 10e-4])
+
+
+def test_host_potential_overlaps_the_sweep(nb, tmp_path):
+    """The host-side external potential is evaluated while the O(N^2) sweep runs (hooks on a side stream):
+    a step costs max(sweep, hook), not their sum.  Per-step times are differences of two runs (S and 3S
+    steps), which removes set-up and the restart-file write."""
+    import time
+    import torch
+
+    class SlowHarmonic:
+        def force(self, pos, t=0.0):
+            time.sleep(0.006)                  # stands for agama's CPU evaluation
+            return -0.5 * np.asarray(pos)
+
+    N, S = 200_000, 8                           # sweep ~15 ms per step > hook 6 ms
+    xv, m = nb.make_plummer_sphere(N, M_total=1e9, a=1.0, seed=3)
+    kw = dict(precision="float32", kernel="plummer", save_snapshots=False, verbose=False)
+
+    def per_step(tag, **extra):
+        ts = []
+        for k in (1, 3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = nb.run_nbody_gpu(xv, m, 0.0, k * S * 1e-4, 1e-4, 0.05, output_dir=str(tmp_path / f"{tag}{k}"),
+                                   **kw, **extra)
+            ts.append(time.perf_counter() - t0)
+            assert np.isfinite(out).all()
+        return (ts[1] - ts[0]) / (2 * S)
+
+    per_step("w", external_potential=SlowHarmonic())       # warm-up of both code paths
+    t_plain = per_step("p", cuda_graph=False)
+    t_hook = per_step("h", external_potential=SlowHarmonic())
+    assert t_hook < t_plain + 0.5 * 0.006, (t_plain, t_hook)   # serialised would be >= t_plain + 6 ms + copies
