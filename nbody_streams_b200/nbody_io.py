@@ -16,6 +16,8 @@ follow reference nbody_streams/nbody_io.py so that its ``ParticleReader`` and
 from __future__ import annotations
 
 import math
+import queue
+import threading
 from pathlib import Path
 
 import numpy as np
@@ -153,3 +155,78 @@ def _update_snapshot_times(output_dir, snap_index: int, time: float) -> None:
     rows[int(snap_index)] = float(time)
     table = np.array(sorted(rows.items()), dtype=float)
     np.savetxt(str(path), table, fmt="%d %.10e", header="snap_index time", comments="# ")
+
+
+class AsyncStateWriter:
+    """Writes snapshots / restart files from device state without stalling the integration loop.
+
+    `submit(kind, xv_dev, job)`: `xv_dev` is a device (N,6) float64 tensor that will not be modified any more
+    (the caller passes a fresh copy); the device->host copy goes to one of two pinned buffers on a side stream
+    and `job(xv_numpy)` — the actual file write — runs in a worker thread once the copy has landed, so neither
+    the D2H transfer nor the (compressing, slow) file write is on the step's critical path.  Restart files
+    overwrite each other, so a queued restart job that has not started when a newer one arrives is dropped.
+    `flush()` blocks until everything submitted has been written (called before run_nbody_gpu returns).
+    """
+
+    def __init__(self, torch, device, n_rows: int):
+        self.torch = torch
+        self.device = device
+        self.stream = torch.cuda.Stream(device)
+        self.buffers = [torch.empty((max(n_rows, 1), 6), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        self.free = queue.Queue()
+        for b in self.buffers:
+            self.free.put(b)
+        self.jobs: queue.Queue = queue.Queue()
+        self.lock = threading.Lock()
+        self.latest_restart = 0
+        self.error: BaseException | None = None
+        self.thread = threading.Thread(target=self._worker, name="nbody-io", daemon=True)
+        self.thread.start()
+
+    def submit(self, kind: str, xv_dev, job) -> None:
+        torch = self.torch
+        buf = self.free.get()                       # back-pressure: at most two copies in flight
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)                # xv_dev was produced on the current stream
+        with torch.cuda.stream(self.stream):
+            buf[: xv_dev.shape[0]].copy_(xv_dev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        xv_dev.record_stream(self.stream)
+        seq = 0
+        if kind == "restart":
+            with self.lock:
+                self.latest_restart += 1
+                seq = self.latest_restart
+        self.jobs.put((kind, seq, buf, xv_dev.shape[0], done, job))
+
+    def _worker(self) -> None:
+        while True:
+            item = self.jobs.get()
+            if item is None:
+                self.jobs.task_done()
+                return
+            kind, seq, buf, n, done, job = item
+            try:
+                stale = kind == "restart" and seq < self.latest_restart
+                if not stale:
+                    done.synchronize()
+                    job(buf[:n].numpy())
+            except BaseException as e:  # noqa: BLE001 - re-raised in flush()
+                self.error = e
+            finally:
+                if kind == "restart" and seq < self.latest_restart:
+                    done.synchronize()               # the copy must have finished before the buffer is reused
+                self.free.put(buf)
+                self.jobs.task_done()
+
+    def flush(self) -> None:
+        self.jobs.join()
+        if self.error is not None:
+            err, self.error = self.error, None
+            raise err
+
+    def close(self) -> None:
+        self.flush()
+        self.jobs.put(None)
+        self.thread.join(timeout=10)

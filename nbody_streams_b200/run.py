@@ -24,7 +24,8 @@ import numpy as np
 from . import _lib
 from ._lib import MODE_BOTH, MODE_FORCE, MODE_POT
 from .fields import EPS2_DEFAULT, G_DEFAULT, KERNEL_MAP, _PRECISION_MAP, DeviceArray
-from .nbody_io import _load_restart, _save_restart, _save_snapshot, _update_snapshot_times
+from .nbody_io import (AsyncStateWriter, _load_restart, _save_restart, _save_snapshot,
+                       _update_snapshot_times)
 from .species import Species
 
 NBODY_UNITS = {"kpc": 1.0, "Msun": 1.0, "kpc / (km/s)": 1.0, "km/s": 1, "G": G_DEFAULT}
@@ -150,6 +151,7 @@ def run_nbody_gpu(
     diagnostics_every: int = 0,
     cuda_graph: bool | None = None,
     exchange: str = "nccl",
+    async_io: bool = True,
 ) -> np.ndarray:
     """GPU direct-summation N-body run with the KDK leapfrog of the reference.
 
@@ -173,7 +175,9 @@ def run_nbody_gpu(
     CUDA graph; default: on for a single rank without hooks and N <= 131072,
     where launch overhead would otherwise dominate the step), ``exchange`` (multi-GPU only:
     ``"nccl"`` all-gathers the packed j-records each step, ``"p2p"`` fuses the exchange into the
-    kick+drift kernel, which stores the refreshed records into every rank's buffer over NVLink).
+    kick+drift kernel, which stores the refreshed records into every rank's buffer over NVLink),
+    ``async_io`` (snapshots / periodic restart files are copied to pinned memory on a side stream and
+    written by a worker thread, so file I/O never stalls the step; False = synchronous as in the reference).
     """
     torch = _lib.require_cuda()   # ImportError when there is no CUDA device / library (reference: "CuPy required")
 
@@ -195,6 +199,12 @@ def run_nbody_gpu(
         softening = np.asarray(softening, dtype=dtype_np)
         if softening.shape[0] != N:
             raise ValueError(f"softening must have length N={N}, got {softening.shape[0]}")
+
+    if save_snapshots:
+        try:
+            import h5py  # noqa: F401  (the reference imports it at module load, run.py:29)
+        except ImportError as e:
+            raise ImportError("h5py is required to write snapshots (save_snapshots=True)") from e
 
     from .engine import DirectEngine, gather_rows, group_info
 
@@ -356,12 +366,29 @@ def run_nbody_gpu(
     def host_state():
         return eng.state_numpy()
 
+    writer = AsyncStateWriter(torch, eng.device, N) if (async_io and is_root) else None
+
+    def write_state(kind, counter, t, step):
+        """Snapshot (kind='snapshot') or periodic restart (kind='restart') of the current state."""
+        if kind == "snapshot":
+            def job(xv_np, counter=counter, t=t):
+                _save_snapshot(xv_np, counter, t, output_path, **_snap_kwargs)
+                _update_snapshot_times(output_path, counter, t)
+        else:
+            def job(xv_np, t=t, step=step, counter=counter):
+                _save_restart(xv_np, t, step, output_path, counter, **_restart_kwargs)
+        if async_io:
+            xv_dev = gather_rows(torch.cat([eng.pos, eng.vel], dim=1), eng.layout, eng.rank, eng.group)
+            if is_root:
+                writer.submit(kind, xv_dev, job)
+        else:
+            xv_np = host_state()
+            if is_root:
+                job(xv_np)
+
     if snapshot_counter < len(snapshot_steps) and snapshot_steps[snapshot_counter] == start_step:
         if save_snapshots:
-            xv_cpu = host_state()
-            if is_root:
-                _save_snapshot(xv_cpu, snapshot_counter, time, output_path, **_snap_kwargs)
-                _update_snapshot_times(output_path, snapshot_counter, time)
+            write_state("snapshot", snapshot_counter, time, start_step)
             if verbose:
                 print(f"Saved snapshot snap: {snapshot_counter:03d} at step {start_step}, time {time:.6e}...")
         snapshot_counter += 1
@@ -392,10 +419,7 @@ def run_nbody_gpu(
 
         while snapshot_counter < len(snapshot_steps) and current_step >= snapshot_steps[snapshot_counter]:
             if save_snapshots:
-                xv_cpu = host_state()
-                if is_root:
-                    _save_snapshot(xv_cpu, snapshot_counter, time, output_path, **_snap_kwargs)
-                    _update_snapshot_times(output_path, snapshot_counter, time)
+                write_state("snapshot", snapshot_counter, time, current_step)
                 if verbose:
                     print(f"Saved snapshot id={snapshot_counter:03d} at step {current_step}, time {time:.6e}...",
                           flush=True)
@@ -425,22 +449,19 @@ def run_nbody_gpu(
                 print(line, flush=True)
 
         if current_step > 0 and (current_step % restart_interval) == 0:
-            xv_cpu = host_state()
-            if is_root:
-                _save_restart(xv_cpu, time, current_step, output_path, snapshot_counter, **_restart_kwargs)
+            write_state("restart", snapshot_counter, time, current_step)
 
     if snapshot_counter < len(snapshot_steps) and snapshot_steps[-1] == total_steps:
         if save_snapshots:
-            xv_cpu = host_state()
             if verbose:
                 print(f"<=Saving final snapshot snap.{snapshot_counter:03d} at step {total_steps}, "
                       f"time {time:.6e}=>")
-            if is_root:
-                _save_snapshot(xv_cpu, snapshot_counter, time, output_path, **_snap_kwargs)
-                _update_snapshot_times(output_path, snapshot_counter, time)
+            write_state("snapshot", snapshot_counter, time, total_steps)
         snapshot_counter += 1
 
     xv_final_cpu = host_state()
+    if writer is not None:
+        writer.close()                      # everything queued is on disk before the final restart is written
     if is_root:
         _save_restart(xv_final_cpu, time, total_steps, output_path, snapshot_counter, **_restart_kwargs)
 
