@@ -67,6 +67,12 @@ def main():
                     f"{np.array_equal(p2p, ovl)}; multicast {'yes' if eng._mc_ptr else 'no'})")
         ok &= bool(e_p2p < 1e-12) and bool(np.array_equal(p2p, ovl))
 
+    # periodic restart files from a sharded run (async writer on rank 0, gather on all ranks)
+    rr = nb.run_nbody_gpu(xv, mass, 0.0, steps * dt, dt, h, output_dir=str(out / "rst"), restart_interval=5, **kw)
+    dist.barrier()
+    rs = np.load(out / "rst" / "restart.npz")
+    ok &= bool(np.array_equal(rr, ovl)) and int(rs["step"]) == steps and bool(np.array_equal(rs["phase_space"], rr))
+
     kw32 = dict(kw, precision="float32_kahan")
     diags = []
     f32 = nb.run_nbody_gpu(xv, mass, 0.0, steps * dt, dt, h, output_dir=str(out / "f32"), diagnostics=diags,
