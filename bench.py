@@ -171,6 +171,12 @@ def run_reference(args):
 
 def main():
     args = parse()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: `python bench.py --gpus N` re-launches itself under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"),
+               str(Path(__file__).resolve()), *sys.argv[1:]]
+        sys.exit(subprocess.call(cmd))
     # keep stdout for the ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
