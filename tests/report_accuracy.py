@@ -8,8 +8,10 @@ from pathlib import Path
 import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
 import nbody_streams_b200 as nb  # noqa: E402
 import oracle  # noqa: E402  (lives under tests/: the oracle is only the checker here)
+import ref_gpu_kernels as refk  # noqa: E402
 
 
 def rel_rms(a, r):
@@ -39,6 +41,16 @@ for kernel in ("plummer", "spline"):
     for prec in ("float32", "float32_kahan", "float64"):
         acc, phi = nb.compute_nbody_forces_potential_gpu(pos, m, 0.01, precision=prec, kernel=kernel)
         out.append(f"| {kernel} | gpu {prec} | {rel_rms(acc[sl], ref):.2e} | {rel_max(acc[sl], ref):.2e} | {rel_rms(phi[sl], pref):.2e} |")
+        if refk.available():   # the reference's own GPU kernel of the same precision, same inputs
+            import torch
+
+            dt = torch.float64 if prec == "float64" else torch.float32
+            pos_t = torch.from_numpy(pos).to(dt).cuda()
+            m_t = torch.from_numpy(m).to(dt).cuda()
+            h_t = torch.full((len(m),), 0.01, dtype=dt, device="cuda")
+            ra = refk.launch("force", prec, pos_t, m_t, h_t, nb.G_DEFAULT, nb.KERNEL_MAP[kernel]).cpu().numpy()
+            rp = refk.launch("potential", prec, pos_t, m_t, h_t, nb.G_DEFAULT, nb.KERNEL_MAP[kernel]).cpu().numpy()
+            out.append(f"| {kernel} | reference GPU kernel {prec} | {rel_rms(ra[sl], ref):.2e} | {rel_max(ra[sl], ref):.2e} | {rel_rms(rp[sl], pref):.2e} |")
 
 out.append("\n# Step rate of run_nbody_gpu (spline, float32_kahan, no snapshots)\n")
 out.append("Per-step time = (t(3S steps) - t(S steps)) / 2S, which removes set-up, the initial force evaluation and the")
