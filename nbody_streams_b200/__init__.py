@@ -10,11 +10,12 @@ from .fields import (G_DEFAULT, KERNEL_MAP, DeviceArray, compute_nbody_forces_gp
 from .run import make_plummer_sphere, run_nbody_gpu
 from .sim import run_simulation
 from .species import PerformanceWarning, Species
+from .unbind import iterative_unbinding
 
 __version__ = "0.1.0"
 
 __all__ = [
     "Species", "PerformanceWarning", "run_simulation", "run_nbody_gpu", "make_plummer_sphere",
     "compute_nbody_forces_gpu", "compute_nbody_potential_gpu", "compute_nbody_forces_potential_gpu",
-    "get_gpu_info", "G_DEFAULT", "KERNEL_MAP", "DeviceArray",
+    "get_gpu_info", "G_DEFAULT", "KERNEL_MAP", "DeviceArray", "iterative_unbinding",
 ]

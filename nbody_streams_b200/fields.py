@@ -232,11 +232,16 @@ def _device_operand(arr_cpu, scalar, original, dtype_t, device):
     return t.contiguous(), 0.0
 
 
-def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, mode, G, eps2, dtype_np, group=None):
+def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, mode, G, eps2, dtype_np, group=None,
+                n_sources=None):
     """pack + sweep + finish on the current stream.  Returns (acc|None, phi|None) torch tensors.
 
     With a torch.distributed `group` of more than one rank every rank packs all N particles, sweeps only
-    the i-rows of its tile-aligned shard and the rows are all-gathered, so each rank returns full arrays."""
+    the i-rows of its tile-aligned shard and the rows are all-gathered, so each rank returns full arrays.
+
+    `n_sources` (None = N): only the j-tiles holding particles [0, n_sources) are swept, i.e. the first
+    n_sources particles are the sources and all N are targets.  The caller passes zero masses for the
+    particles >= n_sources (the tile straddling n_sources is swept whole)."""
     import torch
 
     from .engine import ShardLayout, gather_rows, group_info
@@ -259,7 +264,7 @@ def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, m
         h_ptr, h_dt = (h_t.data_ptr(), _dt_code(h_t)) if h_t is not None else (None, 0)
         acc_ptr = acc.data_ptr() if acc is not None else None
         phi_ptr = phi.data_ptr() if phi is not None else None
-        if world == 1:
+        if world == 1 and n_sources is None:
             ws_bytes = lib.nb_workspace_bytes(prec, N, grid, 1)
             ws = _scratch(device, "workspace", ws_bytes)
             _lib.check(lib.nb_direct(prec, kernel_id, mode, pos_t.data_ptr(), _dt_code(pos_t), mass_ptr, mass_dt,
@@ -273,16 +278,35 @@ def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, m
             if n_i > 0:
                 ws_bytes = lib.nb_workspace_bytes(prec, n_i, grid, 1)
                 ws = _scratch(device, "workspace", ws_bytes)
-                n_tiles = C.c_int(n_pad // 256)
+                n_src = N if n_sources is None else max(0, min(int(n_sources), N))
+                n_tiles = C.c_int(lib.nb_padded_count(n_src) // lib.nb_tile_j())
                 _lib.check(lib.nb_sweep(prec, kernel_id, mode, packed.data_ptr(), N, 0, n_tiles.value, 0, 0,
                                         i_begin, n_i, float(eps2), ws.data_ptr(), ws_bytes, 0, grid, stream))
                 _lib.check(lib.nb_finish(prec, kernel_id, mode, n_i, grid, 1, C.byref(n_tiles), ws.data_ptr(),
                                          float(G), acc_ptr, phi_ptr, stream))
-            if acc is not None:
-                acc = gather_rows(acc, layout, rank, group)
-            if phi is not None:
-                phi = gather_rows(phi, layout, rank, group)
+            if world > 1:
+                if acc is not None:
+                    acc = gather_rows(acc, layout, rank, group)
+                if phi is not None:
+                    phi = gather_rows(phi, layout, rank, group)
     return acc, phi
+
+
+def _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, device):
+    """Masses with zeros from particle n_sources on (test particles), as a device tensor."""
+    import torch
+
+    if n_sources is None:
+        return mass_t, mass_s, None
+    n_src = int(n_sources)
+    if not 0 <= n_src <= N:
+        raise ValueError(f"n_sources must be in [0, N={N}], got {n_sources}")
+    if mass_t is None:
+        m = torch.full((N,), float(mass_s), dtype=_np_to_torch_dtype(dtype_np), device=device)
+    else:
+        m = mass_t.clone()
+    m[n_src:] = 0
+    return m, 0.0, n_src
 
 
 def _prepare(pos, mass, softening, precision, kernel, skip_validation, device):
@@ -337,6 +361,7 @@ def compute_nbody_forces_gpu(
     eps2: float | None = None,
     device=None,
     group=None,
+    n_sources=None,
 ):
     """Direct-summation gravitational accelerations on the GPU.
 
@@ -353,7 +378,10 @@ def compute_nbody_forces_gpu(
     Keyword-only extensions (defaults reproduce the reference call): ``eps2``
     overrides the r^2 regularisation (see ``EPS2_DEFAULT``), ``device`` picks
     the CUDA device, ``group`` (a torch.distributed process group, one rank per
-    GPU) shards the i-particles over its ranks and all-gathers the result.
+    GPU) shards the i-particles over its ranks and all-gathers the result,
+    ``n_sources`` makes only the first n_sources particles gravitating sources
+    (the others are massless test particles and their source tiles are never
+    swept: N x n_sources pair work, used by ``unbind.iterative_unbinding``).
 
     Raises ImportError without a CUDA device / built library, ValueError for
     bad shapes, precision or kernel names, RuntimeError for CUDA failures.
@@ -362,7 +390,8 @@ def compute_nbody_forces_gpu(
     ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
-    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np, group)
+    mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
+    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np, group, n_src)
     if return_cupy:
         return acc.as_subclass(DeviceArray)
     return acc.cpu().numpy()
@@ -381,6 +410,7 @@ def compute_nbody_potential_gpu(
     eps2: float | None = None,
     device=None,
     group=None,
+    n_sources=None,
 ):
     """Gravitational potential at each particle, ``phi_i = G sum_{j != i} m_j Phi(r_ij)``.
 
@@ -393,7 +423,8 @@ def compute_nbody_potential_gpu(
     ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
-    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np, group)
+    mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
+    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np, group, n_src)
     if return_cupy:
         return phi.as_subclass(DeviceArray)
     return phi.cpu().numpy()
@@ -412,6 +443,7 @@ def compute_nbody_forces_potential_gpu(
     eps2: float | None = None,
     device=None,
     group=None,
+    n_sources=None,
 ):
     """Accelerations AND potential from one fused sweep (new; the reference needs two
     O(N^2) passes, run.py:611-634).  Returns ``(acc (N,3), phi (N,))``."""
@@ -419,7 +451,8 @@ def compute_nbody_forces_potential_gpu(
     ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
-    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np, group)
+    mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
+    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np, group, n_src)
     if return_cupy:
         return acc.as_subclass(DeviceArray), phi.as_subclass(DeviceArray)
     return acc.cpu().numpy(), phi.cpu().numpy()

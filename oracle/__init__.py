@@ -171,3 +171,77 @@ def run_nbody_cpu_direct(phase_space, masses, time_start, time_end, dt, softenin
         if record_every and (step % record_every == 0 or step == total_steps):
             diag(step)
     return xv, diags
+
+
+def iterative_unbinding_cpu(pos_dark, vel_dark, mass_dark, pos_star=None, vel_star=None, mass_star=None,
+                            center_position=(), center_velocity=(), recursive_iter_converg=50, softening=0.03,
+                            G=G_DEFAULT, center_on="dark", vel_aperture=5.0, tol_frac_change=0.0001,
+                            return_history=False, top_fraction=0.01, precision="float64", kernel="spline"):
+    """Restatement of the reference's iterative_unbinding with potential_compute_method='direct'
+    (reference utils/main.py:1722-2079; centre :1933-1985, loop :1998-2066, output :2068-2079).
+    phi comes from this oracle's compute_nbody_potential_cpu (reference default precision float64,
+    kernel 'spline', fields.py:1096-1104).  Pinned against the reference's own output in
+    tests/golden/unbinding_*.npz."""
+    pos_dark = np.asarray(pos_dark, dtype=float)
+    vel_dark = np.asarray(vel_dark, dtype=float)
+    n_dark = pos_dark.shape[0]
+    bc = lambda m, n: np.full(n, float(m)) if np.ndim(m) == 0 else np.asarray(m, dtype=float)
+    mass_dark = bc(mass_dark, n_dark)
+    has_stars = pos_star is not None
+    if has_stars:
+        pos_star = np.asarray(pos_star, dtype=float)
+        vel_star = np.asarray(vel_star, dtype=float)
+        mass_star = bc(mass_star, pos_star.shape[0])
+        pos_all = np.vstack((pos_dark, pos_star))
+        vel_all = np.vstack((vel_dark, vel_star))
+        mass_all = np.concatenate((mass_dark, mass_star))
+    else:
+        pos_all, vel_all, mass_all = pos_dark.copy(), vel_dark.copy(), mass_dark.copy()
+    if center_on == "both" or not has_stars:
+        sl = slice(None)
+    elif center_on == "star":
+        sl = slice(n_dark, None)
+    else:
+        sl = slice(None, n_dark)
+
+    def pot(p, m):
+        return compute_nbody_potential_cpu(p, m, softening=softening, G=G, kernel=kernel, precision=precision)
+
+    center_position = np.asarray(center_position, dtype=float)
+    center_velocity = np.asarray(center_velocity, dtype=float)
+    if center_position.size < 3:                                    # main.py:1936-1972
+        phi_c = pot(pos_all, mass_all)[sl]
+        n_pick = max(10, int(len(phi_c) * top_fraction))
+        idx = np.argsort(phi_c)[:n_pick]
+        center_position = np.average(pos_all[sl][idx], axis=0, weights=mass_all[sl][idx])
+    if center_velocity.size < 3:                                    # main.py:1974-1985
+        d2 = np.sum((pos_all[sl] - center_position) ** 2, axis=1)
+        sel = d2 < vel_aperture ** 2
+        if np.any(sel):
+            center_velocity = np.average(vel_all[sl][sel], axis=0, weights=mass_all[sl][sel])
+        else:
+            center_velocity = np.average(vel_all[sl], axis=0, weights=mass_all[sl])
+    pos_rel = pos_all - center_position
+    vel_rel = vel_all - center_velocity
+    mask = np.ones(len(pos_all), dtype=bool)
+    hist = []
+    energies = None
+    for _ in range(recursive_iter_converg):                         # main.py:1998-2066
+        if int(mask.sum()) < 5:
+            break
+        phi = pot(pos_rel, mass_all * mask)
+        energies = phi + 0.5 * np.sum(vel_rel ** 2, axis=1)
+        bound = energies < 0
+        hist.append(bound.copy())
+        frac = np.mean(bound != mask)
+        mask = bound
+        if frac < tol_frac_change:
+            break
+    res = [mask[:n_dark].astype(int)]
+    if has_stars:
+        res.append(mask[n_dark:].astype(int))
+    if return_history:
+        res.append([h[:n_dark] for h in hist])
+        if has_stars:
+            res.append([h[n_dark:] for h in hist])
+    return tuple(res), center_position, center_velocity

@@ -81,6 +81,20 @@ def main():
     msgs.append(f"run float32_kahan vs float64: {e32:.2e}; diagnostics rows {len(diags)}")
     ok &= bool(e32 < 1e-4) and len(diags) == 3
 
+    # iterative unbinding with the target rows sharded over the ranks: masks identical on every rank and
+    # equal to the single-GPU result
+    from nbody_streams_b200.unbind import iterative_unbinding
+
+    rng = np.random.default_rng(9)
+    sat = xv[:7000].copy()
+    pick = rng.random(7000) < 0.3
+    sat[pick, 3:] *= 3.0
+    ukw = dict(potential_compute_method="direct_gpu", softening=0.05, verbose=False, precision="float64")
+    (b1,), c1, v1 = iterative_unbinding(sat[:, :3], sat[:, 3:], md, **ukw)
+    (bw,), cw, vw = iterative_unbinding(sat[:, :3], sat[:, 3:], md, group=dist.group.WORLD, **ukw)
+    msgs.append(f"unbinding: bound {int(b1.sum())}/7000, sharded equal {np.array_equal(b1, bw)}")
+    ok &= bool(np.array_equal(b1, bw)) and bool(np.allclose(c1, cw, rtol=1e-12)) and 0 < b1.sum() < 7000
+
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
