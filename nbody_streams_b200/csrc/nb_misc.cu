@@ -107,16 +107,17 @@ __global__ void finish_kernel(const FinishArgs a, OT* __restrict__ acc, OT* __re
         const PT* part = reinterpret_cast<const PT*>(slot + a.part_off);
         const long long total = static_cast<long long>(a.n_ib) * n_jt;
         const long long ub = static_cast<long long>(ib) * n_jt, ue = ub + n_jt;
-        // first CTA whose unit range contains ub
-        int c = static_cast<int>((ub * a.grid) / total);
+        // Walk the pieces of [ub, ue) in ascending unit (= ascending CTA) order.  The CTA holding unit u is the
+        // largest c with unit_begin(c) <= u; computing it directly skips the CTAs with an empty range (most of
+        // the grid when there are fewer units than CTAs, i.e. N of a few thousand).
+        const bool dense = total >= a.grid;          // every CTA owns at least one unit: the next piece is CTA c+1
+        int c = static_cast<int>(((ub + 1) * a.grid + total - 1) / total) - 1;
         if (c >= a.grid) c = a.grid - 1;
-        while (c > 0 && unit_begin(total, c, a.grid) > ub) --c;
-        while (c + 1 < a.grid && unit_begin(total, c + 1, a.grid) <= ub) ++c;
-        for (; c < a.grid; ++c) {
-            const long long cb = unit_begin(total, c, a.grid), ce = unit_begin(total, c + 1, a.grid);
-            if (cb >= ue) break;
+        long long cb = unit_begin(total, c, a.grid);
+        long long u = ub;
+        while (u < ue) {
+            const long long ce = unit_begin(total, c + 1, a.grid);
             const long long sb = cb > ub ? cb : ub, se = ce < ue ? ce : ue;
-            if (se <= sb) continue;   // CTA with an empty range
             PT v;
             if (sb == ub && se == ue) v = full[static_cast<size_t>(ib) * a.IB + li];
             else v = part[(static_cast<size_t>(c) * 2 + (sb == cb ? 0 : 1)) * a.IB + li];
@@ -124,6 +125,15 @@ __global__ void finish_kernel(const FinishArgs a, OT* __restrict__ acc, OT* __re
             sy += static_cast<double>(v.y);
             sz += static_cast<double>(v.z);
             sp += static_cast<double>(v.w);
+            u = se;
+            if (u >= ue) break;
+            if (dense) {
+                ++c;
+                cb = ce;
+            } else {
+                c = static_cast<int>(((u + 1) * a.grid + total - 1) / total) - 1;
+                cb = unit_begin(total, c, a.grid);
+            }
         }
     }
     if (acc) {
@@ -334,7 +344,7 @@ int nb_launch_finish(int prec, long long n_i, int grid, int IB, int n_sweeps, co
     a.n_ib = static_cast<int>((n_i + IB - 1) / IB);
     a.n_i = n_i;
     a.G = G;
-    const int threads = 256;
+    const int threads = n_i >= 148 * 256 ? 256 : 64;      // small N: spread the rows over more SMs
     const unsigned blocks = static_cast<unsigned>((n_i + threads - 1) / threads);
     if (prec == NB_PREC_F32)
         finish_kernel<float4, float><<<blocks, threads, 0, st>>>(a, static_cast<float*>(acc), static_cast<float*>(phi));

@@ -1,8 +1,7 @@
 #!/usr/bin/env python3
-"""Accuracy of the three precisions against the float64 oracle at full bench size (row subset), and
-small-N step rate of run_nbody_gpu.  Writes gpurun_out/accuracy.md."""
+"""Accuracy of the three precisions (and of the reference's own GPU kernels) against the float64 oracle at
+full bench size (row subset).  Writes gpurun_out/accuracy.md.  (Step rates: tools/step_rate.py.)"""
 import sys
-import time
 from pathlib import Path
 
 import numpy as np
@@ -52,22 +51,6 @@ for kernel in ("plummer", "spline"):
             rp = refk.launch("potential", prec, pos_t, m_t, h_t, nb.G_DEFAULT, nb.KERNEL_MAP[kernel]).cpu().numpy()
             out.append(f"| {kernel} | reference GPU kernel {prec} | {rel_rms(ra[sl], ref):.2e} | {rel_max(ra[sl], ref):.2e} | {rel_rms(rp[sl], pref):.2e} |")
 
-out.append("\n# Step rate of run_nbody_gpu (spline, float32_kahan, no snapshots)\n")
-out.append("Per-step time = (t(3S steps) - t(S steps)) / 2S, which removes set-up, the initial force evaluation and the")
-out.append("final restart.npz write (np.savez_compressed, ~3 ms per 10k particles) that every run pays once.\n")
-out.append("| N | S | ms/step | Gint/s | one-off overhead ms |")
-out.append("|---:|---:|---:|---:|---:|")
-for N, steps in ((1_000, 300), (10_000, 300), (40_000, 100), (100_000, 40), (262_144, 10)):
-    xs, ms_ = nb.make_plummer_sphere(N, M_total=1e9, a=1.0, seed=1)
-    kw = dict(save_snapshots=False, verbose=False, output_dir="/tmp/acc_out")
-    nb.run_nbody_gpu(xs, ms_, 0.0, 5e-4, 1e-4, 0.05, **kw)
-    ts = []
-    for k in (1, 3):
-        t0 = time.perf_counter()
-        nb.run_nbody_gpu(xs, ms_, 0.0, k * steps * 1e-4, 1e-4, 0.05, **kw)
-        ts.append(time.perf_counter() - t0)
-    per = (ts[1] - ts[0]) / (2 * steps)
-    out.append(f"| {N} | {steps} | {per * 1e3:.3f} | {N * N / per / 1e9:.1f} | {(ts[0] - steps * per) * 1e3:.1f} |")
 Path("gpurun_out").mkdir(exist_ok=True)
 Path("gpurun_out/accuracy.md").write_text("\n".join(out) + "\n")
 print("\n".join(out))
