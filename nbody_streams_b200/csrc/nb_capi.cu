@@ -28,21 +28,23 @@ using namespace nb;
 
 namespace {
 
-int g_variant_f32 = -1;   // -1: read NB_F32_VARIANT / NB_F64_VARIANT from the environment once
-int g_variant_f64 = -1;
+constexpr int VARIANT_UNREAD = -2;   // NB_F32_VARIANT / NB_F64_VARIANT not looked at yet
+constexpr int VARIANT_AUTO   = -1;   // pick per (kernel, mode): the measured best (see eff_variant)
+int g_variant_f32 = VARIANT_UNREAD;
+int g_variant_f64 = VARIANT_UNREAD;
 
 int env_variant(const char* name, int nmax) {
     const char* s = std::getenv(name);
-    if (!s) return 0;
+    if (!s || !*s) return VARIANT_AUTO;
     const int v = std::atoi(s);
-    return (v >= 0 && v < nmax) ? v : 0;
+    return (v >= 0 && v < nmax) ? v : VARIANT_AUTO;
 }
 int cur_variant_f32() {
-    if (g_variant_f32 < 0) g_variant_f32 = env_variant("NB_F32_VARIANT", NV_F32);
+    if (g_variant_f32 == VARIANT_UNREAD) g_variant_f32 = env_variant("NB_F32_VARIANT", NV_F32);
     return g_variant_f32;
 }
 int cur_variant_f64() {
-    if (g_variant_f64 < 0) g_variant_f64 = env_variant("NB_F64_VARIANT", NV_F64);
+    if (g_variant_f64 == VARIANT_UNREAD) g_variant_f64 = env_variant("NB_F64_VARIANT", NV_F64);
     return g_variant_f64;
 }
 
@@ -51,13 +53,19 @@ bool valid_mode(int m) { return m == NB_MODE_FORCE || m == NB_MODE_POT || m == N
 bool valid_kid(int k) { return k >= 0 && k <= 4; }
 
 // tuning variants other than 0 exist only for plummer and spline
-int eff_variant(int prec, int kid) {
+int eff_variant(int prec, int kid, int mode) {
     const bool allv = (kid == NB_KERNEL_PLUMMER || kid == NB_KERNEL_SPLINE);
     if (!allv) return 0;
-    return prec == NB_PREC_F64 ? cur_variant_f64() : cur_variant_f32();
+    const int v = prec == NB_PREC_F64 ? cur_variant_f64() : cur_variant_f32();
+    if (v != VARIANT_AUTO) return v;
+    // measured on B200 (profiles/r01_probe_variant_sweep.log): variant 0 everywhere except
+    //   float64 spline: 4 i per thread at 3 CTAs/SM, +3 % (more independent DFMA chains per warp)
+    //   float32 plummer potential-only: 1 i-pair per thread at 8 CTAs/SM, +10 % (MUFU-bound, wants warps)
+    if (prec == NB_PREC_F64) return kid == NB_KERNEL_SPLINE ? 1 : 0;
+    return (kid == NB_KERNEL_PLUMMER && mode == NB_MODE_POT) ? 2 : 0;
 }
-int block_i_for(int prec, int kid) {
-    const int v = eff_variant(prec, kid);
+int block_i_for(int prec, int kid, int mode) {
+    const int v = eff_variant(prec, kid, mode);
     return prec == NB_PREC_F64 ? THREADS * variant_f64(v).ni : THREADS * 2 * variant_f32(v).np;
 }
 // workspace sizing must not depend on the softening kernel: use the largest i-block of the precision
@@ -72,7 +80,7 @@ int block_i_max(int prec) {
 }
 
 int dispatch(int prec, int kid, int mode, int op, const SweepArgs* a, int grid, int* out, cudaStream_t st) {
-    const int v = eff_variant(prec, kid);
+    const int v = eff_variant(prec, kid, mode);
     if (prec == NB_PREC_F64) {
         switch (kid) {
             case 0: return nb_dispatch_f64_k0(mode, v, op, a, grid, out, st);
@@ -160,10 +168,10 @@ int nb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* mem_tota
 /* tuning (not part of the reference-facing surface): select a compiled variant */
 int nb_set_variant(int prec, int variant) {
     if (prec == NB_PREC_F64) {
-        if (variant < 0 || variant >= NV_F64) return NB_E_INVALID_ARG;
+        if (variant < VARIANT_AUTO || variant >= NV_F64) return NB_E_INVALID_ARG;
         g_variant_f64 = variant;
     } else {
-        if (variant < 0 || variant >= NV_F32) return NB_E_INVALID_ARG;
+        if (variant < VARIANT_AUTO || variant >= NV_F32) return NB_E_INVALID_ARG;
         g_variant_f32 = variant;
     }
     return 0;
@@ -224,7 +232,7 @@ int nb_sweep(int prec, int kernel_id, int mode, const void* packed, long n_j, in
     if (workspace_bytes < L.slot_bytes * static_cast<size_t>(slot + 1)) return NB_E_WORKSPACE;
     if (n_i == 0) return 0;
 
-    const int IB = block_i_for(prec, kernel_id);
+    const int IB = block_i_for(prec, kernel_id, mode);
     SweepArgs a;
     a.packed = static_cast<const unsigned char*>(packed);
     a.n_j = n_j;
@@ -255,7 +263,7 @@ int nb_finish(int prec, int kernel_id, int mode, long n_i, int grid, int n_sweep
     if (!(mode & NB_MODE_FORCE)) acc = nullptr;
     if (!(mode & NB_MODE_POT)) phi = nullptr;
     const SlotLayout L = slot_layout(prec, n_i, grid);
-    return nb_launch_finish(prec, n_i, grid, block_i_for(prec, kernel_id), n_sweeps, n_jt, workspace, L.slot_bytes,
+    return nb_launch_finish(prec, n_i, grid, block_i_for(prec, kernel_id, mode), n_sweeps, n_jt, workspace, L.slot_bytes,
                             L.part_off, G, acc, phi, static_cast<cudaStream_t>(stream));
 }
 

@@ -287,19 +287,24 @@ def test_results_independent_of_tuning_variant(nb):
     ref = oracle.compute_nbody_forces_cpu(xv[:, :3], m, 0.05, kernel="plummer")
     try:
         pref = oracle.compute_nbody_potential_cpu(xv[:, :3], m, 0.05, kernel="plummer")
-        for v in range(4):
-            lib.nb_set_variant(0, v)
+        for v in (-1, 0, 1, 2, 3):            # -1 = automatic (per kernel and mode)
+            assert lib.nb_set_variant(0, v) == 0
             for kern, r_a, r_p in (("plummer", ref, pref),):
                 acc, phi = nb.compute_nbody_forces_potential_gpu(xv[:, :3], m, 0.05, precision="float32_kahan",
                                                                  kernel=kern)
                 assert rel_rms(acc, r_a) <= TOL32 and rel_rms(phi, r_p) <= TOL32
-        for v in range(3):
-            lib.nb_set_variant(2, v)
+                phi_only = nb.compute_nbody_potential_gpu(xv[:, :3], m, 0.05, precision="float32_kahan", kernel=kern)
+                assert rel_rms(phi_only, r_p) <= TOL32
+        sref = oracle.compute_nbody_forces_cpu(xv[:, :3], m, 0.05, kernel="spline")
+        for v in (-1, 0, 1, 2):
+            assert lib.nb_set_variant(2, v) == 0
             acc = nb.compute_nbody_forces_gpu(xv[:, :3], m, 0.05, precision="float64", kernel="plummer")
             assert rel_max(acc, ref) <= TOL64
+            acc = nb.compute_nbody_forces_gpu(xv[:, :3], m, 0.05, precision="float64", kernel="spline")
+            assert rel_max(acc, sref) <= TOL64
     finally:
-        lib.nb_set_variant(0, 0)
-        lib.nb_set_variant(2, 0)
+        lib.nb_set_variant(0, -1)
+        lib.nb_set_variant(2, -1)
 
 
 def test_deterministic_bitwise(nb):

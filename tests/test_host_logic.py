@@ -195,6 +195,7 @@ def test_library_host_side_queries():
     assert lib.nb_workspace_bytes(_lib.PREC_F32_COMP, 1000, 592, 2) == 2 * lib.nb_workspace_bytes(_lib.PREC_F32_COMP, 1000, 592, 1)
     assert lib.nb_error_string(0) == b"ok" and b"invalid" in lib.nb_error_string(-1)
     assert lib.nb_set_variant(0, 99) == -1 and lib.nb_set_variant(0, 0) == 0 and lib.nb_get_variant(0) == 0
+    assert lib.nb_set_variant(0, -2) == -1 and lib.nb_set_variant(0, -1) == 0 and lib.nb_get_variant(0) == -1   # automatic
     assert lib.nb_energy_workspace_bytes(10_000) >= 8 * 8
     # argument validation happens before any CUDA call
     assert lib.nb_pack(7, 0, None, 0, None, 0, None, 0, 0.0, None, 0, 0.0, 0, 0, 0.0, None) == -1

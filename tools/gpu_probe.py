@@ -77,7 +77,7 @@ def main():
                     gi = N * N / ms / 1e6
                     res[f"v{v}_{kernel}_{prec}_{mname}"] = {"ms": ms, "gint_s": gi}
                     print(f"v{v} {kernel:8s} {prec:14s} {mname:5s} {ms:9.3f} ms  {gi:9.1f} Gint/s", flush=True)
-    lib.nb_set_variant(0, 0)
+    lib.nb_set_variant(0, -1)
     for v in range(1):
         lib.nb_set_variant(2, v)
         for kernel in ("plummer", "spline"):
@@ -86,7 +86,7 @@ def main():
                 gi = N * N / ms / 1e6
                 res[f"f64_v{v}_{kernel}_{mname}"] = {"ms": ms, "gint_s": gi}
                 print(f"f64 v{v} {kernel:8s} {mname:5s} {ms:9.3f} ms  {gi:9.1f} Gint/s", flush=True)
-    lib.nb_set_variant(2, 0)
+    lib.nb_set_variant(2, -1)
     for kernel in ("newtonian", "dehnen_k1", "dehnen_k2"):
         ms = time_direct(pos_t, float(m[0]), 0.01, N, "float32", kernel, 1)
         res[f"v0_{kernel}_float32_force"] = {"ms": ms, "gint_s": N * N / ms / 1e6}
