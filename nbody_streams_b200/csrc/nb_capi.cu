@@ -58,11 +58,12 @@ int eff_variant(int prec, int kid, int mode) {
     if (!allv) return 0;
     const int v = prec == NB_PREC_F64 ? cur_variant_f64() : cur_variant_f32();
     if (v != VARIANT_AUTO) return v;
-    // measured on B200 (profiles/r01_probe_variant_sweep.log): variant 0 everywhere except
+    // measured on B200 with this build (profiles/r01_variant_sweep.log): variant 0 everywhere except
     //   float64 spline: 4 i per thread at 3 CTAs/SM, +3 % (more independent DFMA chains per warp)
-    //   float32 plummer potential-only: 1 i-pair per thread at 8 CTAs/SM, +10 % (MUFU-bound, wants warps)
+    //   float32 plummer force-only / potential-only: 1 i-pair per thread at 8 CTAs/SM, +4.5 % / +4 %
+    //   (the fused force+potential loop needs the registers of the 2-pair blocking and stays on variant 0)
     if (prec == NB_PREC_F64) return kid == NB_KERNEL_SPLINE ? 1 : 0;
-    return (kid == NB_KERNEL_PLUMMER && mode == NB_MODE_POT) ? 2 : 0;
+    return (kid == NB_KERNEL_PLUMMER && mode != NB_MODE_BOTH) ? 2 : 0;
 }
 int block_i_for(int prec, int kid, int mode) {
     const int v = eff_variant(prec, kid, mode);

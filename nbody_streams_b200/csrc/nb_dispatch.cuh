@@ -16,8 +16,10 @@ constexpr int NV_F32 = 4;
 constexpr int NV_F64 = 3;
 __host__ __device__ constexpr VariantF32 variant_f32(int v) {
     // 0: default (2 i-pairs/thread, 5 CTAs/SM, 4 j per iteration)   1: 4 CTAs/SM, 124 registers
-    // 2: 1 i-pair/thread, 8 CTAs/SM (best for potential-only)       3: decoupled warps (no per-tile __syncthreads)
-    // measured on B200 (profiles/r01_probe_variant_sweep.log): all within 3 % for force sweeps, 0 is best overall
+    // 2: 1 i-pair/thread, 8 CTAs/SM (best for force-only and potential-only plummer)
+    // 3: decoupled warps (no per-tile __syncthreads)
+    // measured on B200 (profiles/r01_variant_sweep.log): within 5 % of each other; nb_capi.cu picks per (kernel, mode).
+    // Also tried: 1 i-pair at 6 and 7 CTAs/SM (80 / 64 registers) — no better than 0 or 2 in any mode.
     return v == 1 ? VariantF32{2, 4, 4, false} : v == 2 ? VariantF32{1, 8, 4, false}
          : v == 3 ? VariantF32{2, 5, 4, true} : VariantF32{2, 5, 4, false};
 }

@@ -78,7 +78,7 @@ def main():
                     res[f"v{v}_{kernel}_{prec}_{mname}"] = {"ms": ms, "gint_s": gi}
                     print(f"v{v} {kernel:8s} {prec:14s} {mname:5s} {ms:9.3f} ms  {gi:9.1f} Gint/s", flush=True)
     lib.nb_set_variant(0, -1)
-    for v in range(1):
+    for v in range(3):
         lib.nb_set_variant(2, v)
         for kernel in ("plummer", "spline"):
             for mode, mname in ((1, "force"), (3, "both")):
