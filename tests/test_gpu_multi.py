@@ -22,3 +22,34 @@ def test_sharded_run_matches_single_gpu(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=550)
     res = (tmp_path / "result.txt").read_text() if (tmp_path / "result.txt").exists() else ""
     assert r.returncode == 0 and res.startswith("OK"), f"{res}\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}"
+
+
+def test_device_keyword_selects_a_non_current_gpu(tmp_path):
+    """Single process, `device=` pointing at a GPU that is not the current one: same bits as on GPU 0."""
+    import numpy as np
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import nbody_streams_b200 as nb
+
+    xv, m = nb.make_plummer_sphere(6001, M_total=1e9, a=1.0, seed=4)
+    torch.cuda.set_device(0)
+    a0, p0 = nb.compute_nbody_forces_potential_gpu(xv[:, :3], m, 0.05)
+    a1, p1 = nb.compute_nbody_forces_potential_gpu(xv[:, :3], m, 0.05, device=torch.device("cuda", 1))
+    assert np.array_equal(a0, a1) and np.array_equal(p0, p1)
+    d1 = nb.compute_nbody_forces_gpu(xv[:, :3], m, 0.05, device=torch.device("cuda", 1), return_cupy=True)
+    assert d1.device.index == 1 and np.array_equal(d1.get(), a0)
+    kw = dict(precision="float64", kernel="spline", save_snapshots=False, verbose=False)
+    r0 = nb.run_nbody_gpu(xv, m, 0.0, 5e-4, 1e-4, 0.05, output_dir=str(tmp_path / "d0"), **kw)
+    r1 = nb.run_nbody_gpu(xv, m, 0.0, 5e-4, 1e-4, 0.05, output_dir=str(tmp_path / "d1"), device=torch.device("cuda", 1),
+                          **kw)
+    assert np.array_equal(r0, r1)
+    from nbody_streams_b200.unbind import iterative_unbinding
+
+    (b0,), _, _ = iterative_unbinding(xv[:, :3], 2.0 * xv[:, 3:], m, potential_compute_method="direct_gpu",
+                                      verbose=False)
+    (b1,), _, _ = iterative_unbinding(xv[:, :3], 2.0 * xv[:, 3:], m, potential_compute_method="direct_gpu",
+                                      verbose=False, device="cuda:1")
+    assert np.array_equal(b0, b1)
+    assert torch.cuda.current_device() == 0
