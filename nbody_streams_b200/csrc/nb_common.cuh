@@ -171,6 +171,28 @@ __device__ __forceinline__ T spline_phi_inside(T r, T h) {
            hinv;
 }
 
+// Division-free form of the two functions above for the sweeps' exact paths: given d = r^2 (> 0 or 0),
+// rinv = 1/r and hinv = 1/h (both from the kernels' reciprocal square roots) it returns w (the
+// 1/r^3-equivalent) and p (the +1/r-equivalent, i.e. minus spline_phi_inside).  Same polynomials; the
+// -(1/15)/q^3 and (1/15)/q terms of the outer branch are written as (1/15) rinv^3 and (1/15) rinv.
+// d == 0 (coincident particles with eps2 = 0) takes the q -> 0 limit like the reference's q < 1e-8 case.
+template <typename T>
+__device__ __forceinline__ void spline_inside(const T d, const T rinv, const T hinv, T& w, T& p) {
+    const T r     = d > T(0) ? d * rinv : T(0);
+    const T q     = r * hinv;
+    const T q2    = q * q;
+    const T h3inv = hinv * hinv * hinv;
+    if (q <= T(0.5)) {
+        w = h3inv * (T(10.666666666666666) + q2 * (T(32.0) * q - T(38.4)));
+        p = (T(2.8) - q2 * (T(5.333333333333333) + (q2 * q2) * (T(6.4) * q - T(9.6)))) * hinv;
+    } else {
+        const T k = T(0.06666666666666667) * rinv;
+        w = h3inv * (T(21.333333333333333) + q * (T(-48.0) + q * (T(38.4) - T(10.666666666666667) * q))) -
+            k * (rinv * rinv);
+        p = (T(3.2) - q2 * (T(10.666666666666666) + q * (T(-16.0) + q * (T(9.6) - T(2.1333333333333333) * q)))) * hinv - k;
+    }
+}
+
 // integer helpers for the stream-K split: CTA c owns units [unit_begin(c), unit_begin(c+1))
 __host__ __device__ __forceinline__ long long unit_begin(long long total, int c, int grid) {
     return (total * (long long)c) / (long long)grid;

@@ -126,17 +126,18 @@ __device__ __forceinline__ void spline_fix(const float xj, const float yj, const
     const float h2 = fmaxf(cj, ci);
     if (valid && d < h2) {
         const float mj = UM ? 1.f : mj_in;
-        const float rc = rsqrt_approx(h2);   // what the packed path used: rsqrt(max(d, h2))
+        const float rc = rsqrt_approx(h2);   // what the packed path used: rsqrt(max(d, h2)); also 1/h
         const float mr = UM ? rc : mj * rc;
-        const float r = sqrtf(d), h = sqrtf(h2);
+        float w, p;
+        spline_inside<float>(d, rsqrt_approx(d), rc, w, p);
         if (MODE & NB_MODE_FORCE) {
             const float f_main = mr * (rc * rc);
-            const float f      = fmaf(mj, spline_w_inside<float>(r, h), -f_main);
+            const float f      = fmaf(mj, w, -f_main);
             ax = fmaf(f, dx, ax);
             ay = fmaf(f, dy, ay);
             az = fmaf(f, dz, az);
         }
-        if (MODE & NB_MODE_POT) sp += fmaf(mj, -spline_phi_inside<float>(r, h), -mr);
+        if (MODE & NB_MODE_POT) sp += fmaf(mj, p, -mr);
     }
 }
 
@@ -294,12 +295,10 @@ __device__ __forceinline__ void spline_exact(const float xj, const float yj, con
     const float h2 = fmaxf(cj, ci);
     const float mj = UM ? 1.f : mj_in;
     float w, p;
+    const float ri = rsqrt_approx(d);
     if (d < h2) {
-        const float r = sqrtf(d), h = sqrtf(h2);
-        w = spline_w_inside<float>(r, h);
-        p = -spline_phi_inside<float>(r, h);
+        spline_inside<float>(d, ri, rsqrt_approx(h2), w, p);
     } else {
-        const float ri = rsqrt_approx(d);
         p = ri;
         w = ri * (ri * ri);
     }

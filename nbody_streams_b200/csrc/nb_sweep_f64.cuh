@@ -64,9 +64,10 @@ __device__ __forceinline__ void pair_f64(const double xj, const double yj, const
         if (KID == NB_KERNEL_SPLINE) {
             if (inside) {   // exact Monaghan spline instead of the clamped Newtonian value
                 const double dr = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
-                const double r = sqrt(dr), h = sqrt(h2);
-                if (MODE & NB_MODE_FORCE) f = mj * spline_w_inside<double>(r, h);
-                if (MODE & NB_MODE_POT) p = -mj * spline_phi_inside<double>(r, h);
+                double w, ph;
+                spline_inside<double>(dr, rsqrt_f64(dr), rinv /* = 1/h: d was clamped to h2 */, w, ph);
+                if (MODE & NB_MODE_FORCE) f = mj * w;
+                if (MODE & NB_MODE_POT) p = mj * ph;
             }
         }
         if (MODE & NB_MODE_POT) sp += p;
@@ -139,12 +140,10 @@ __device__ __forceinline__ void spline_exact_f64(const double xj, const double y
     const double h2 = fmax(cj, ci);
     const double mj = UM ? 1.0 : mj_in;
     double w, p;
+    const double ri = rsqrt_f64(d);
     if (d < h2) {
-        const double r = sqrt(d), h = sqrt(h2);
-        w = spline_w_inside<double>(r, h);
-        p = -spline_phi_inside<double>(r, h);
+        spline_inside<double>(d, ri, rsqrt_f64(h2), w, p);
     } else {
-        const double ri = rsqrt_f64(d);
         p = ri;
         w = ri * (ri * ri);
     }
