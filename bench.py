@@ -281,7 +281,7 @@ def main():
         "sweep_share_of_step": sweep_total_ms / elapsed_ms,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture of this
         # command at the default workload (profiles/r01_ncu_sweep_f32_bench_n1m.md); null for other shapes
-        "traffic": 23734272 if (N == 1_000_000 and world == 1 and args.precision != "float64") else None,
+        "traffic": 33459712 if (N == 1_000_000 and world == 1 and args.precision != "float64") else None,
         "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic bytes per launch: 20 MB read + 32 MB "
                         "partial sums written (absorbed by L2) for 2e13 algorithmic flop -> FP32-pipe bound",
     }
