@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-]
+] + os.environ.get("NB_EXTRA_NVCC_FLAGS", "").split()     # experiments only, e.g. -DNB_ACC_SCALAR
 
 
 def _nvcc() -> str:
