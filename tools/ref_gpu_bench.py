@@ -45,7 +45,7 @@ for precision in ("float32", "float32_kahan", "float64"):
             t_ref = med(lambda: ref.launch(kind, precision, pos_t, mass_t, h_t, nb.G_DEFAULT, kid),
                         reps=3 if precision == "float64" else 5)
             t_our = med(lambda: _run_direct(pos_t, mass_t, 0.0, h_t, 0.0, N, prec, kid, mode, nb.G_DEFAULT, 1e-15, dtn))
-            rows.append(f"| {kind} | {precision} | {kernel} | {t_ref:.2f} | {N*N/t_ref/1e6:.0f} | {t_our:.2f} | "
+            rows.append(f"| {kind} | {precision} | {kernel} | {t_ref:.3f} | {N*N/t_ref/1e6:.0f} | {t_our:.3f} | "
                         f"{N*N/t_our/1e6:.0f} | {t_ref/t_our:.2f}x |")
             print(rows[-1], flush=True)
 Path("gpurun_out").mkdir(exist_ok=True)
