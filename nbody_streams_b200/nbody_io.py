@@ -75,8 +75,9 @@ def _save_snapshot(phase_space, snap_index, time, output_dir, *, species=None, n
                 grp.create_dataset("N", data=int(s.N))
                 for values, scalar_key, array_key in ((_per_particle(s.mass, s.N), "m", "m_array"),
                                                       (_per_particle(s.softening, s.N), "eps", "eps_array")):
-                    if values.size and np.all(values == values[0]):
-                        grp.create_dataset(scalar_key, data=float(values[0]))
+                    # the reference's _is_uniform: equal to the first element within rtol 1e-10 (nbody_io.py:36-45)
+                    if values.size and np.allclose(values, float(values.flat[0]), rtol=1e-10, atol=0.0):
+                        grp.create_dataset(scalar_key, data=float(values.flat[0]))
                     else:
                         grp.create_dataset(array_key, data=values, compression="gzip")
         else:

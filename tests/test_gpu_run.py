@@ -300,3 +300,69 @@ def test_async_io_restart_files_match_synchronous(nb, tmp_path):
     c = nb.run_nbody_gpu(xv, m, 0.0, 10e-4, 1e-4, 0.05, output_dir=str(tmp_path / "part"), async_io=True,
                          continue_run=True, **kw)
     assert np.abs(c - a).max() / np.abs(a).max() < 1e-13
+
+
+# ---- snapshots (HDF5 schema through tests/fake_h5py.py: h5py is not installed in this image) ----------------
+
+@pytest.fixture
+def h5(monkeypatch):
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import fake_h5py
+
+    monkeypatch.setitem(sys.modules, "h5py", fake_h5py)
+    return fake_h5py
+
+
+@pytest.mark.parametrize("async_io", [True, False])
+def test_snapshots_follow_the_reference_schedule(nb, tmp_path, h5, async_io):
+    """snapshots=5 over 20 steps -> np.round(np.linspace(0, 20, 5)) = steps 0, 5, 10, 15, 20 (run.py:571-574);
+    snap.000 is the initial state, the last one the returned final state; times in the attrs and snapshot.times."""
+    xv, m = nb.make_plummer_sphere(3001, M_total=1e9, a=1.0, seed=17)
+    out = tmp_path / "run"
+    kw = dict(precision="float64", kernel="spline", verbose=False, async_io=async_io)
+    final = nb.run_nbody_gpu(xv, m, 0.0, 20e-4, 1e-4, 0.05, output_dir=str(out), save_snapshots=True, snapshots=5, **kw)
+    flat = h5.flatten(out / "snapshot.h5")
+    names = sorted(k for k in flat if k.startswith("/snapshots/snap.") and "#" not in k)
+    assert names == [f"/snapshots/snap.{i:03d}" for i in range(5)]
+    assert np.array_equal(flat["/snapshots/snap.000"], xv)
+    assert np.array_equal(flat["/snapshots/snap.004"], final)
+    for i, step in enumerate((0, 5, 10, 15, 20)):
+        assert float(flat[f"/snapshots@snap_time.{i:03d}"]) == pytest.approx(step * 1e-4, rel=1e-12, abs=1e-18)
+    assert int(flat["/properties/dark/N"]) == 3001 and float(flat["/properties/dark/m"]) == float(m[0])
+    times = np.loadtxt(out / "snapshot.times")
+    assert times.shape == (5, 2) and np.allclose(times[:, 1], np.arange(0, 21, 5) * 1e-4)
+    # the intermediate snapshot equals a run that stops there
+    mid = nb.run_nbody_gpu(xv, m, 0.0, 10e-4, 1e-4, 0.05, output_dir=str(tmp_path / "mid"), save_snapshots=False, **kw)
+    assert np.array_equal(flat["/snapshots/snap.002"], mid)
+    # existing snapshots: refused unless overwrite / continue_run (run.py:513-526)
+    with pytest.raises(FileExistsError):
+        nb.run_nbody_gpu(xv, m, 0.0, 2e-4, 1e-4, 0.05, output_dir=str(out), save_snapshots=True, **kw)
+    nb.run_nbody_gpu(xv, m, 0.0, 2e-4, 1e-4, 0.05, output_dir=str(out), save_snapshots=True, snapshots=2, overwrite=True,
+                     **kw)
+    flat2 = h5.flatten(out / "snapshot.h5")
+    assert sorted(k for k in flat2 if k.startswith("/snapshots/snap.") and "#" not in k) == \
+        ["/snapshots/snap.000", "/snapshots/snap.001"]
+
+
+def test_multi_species_snapshots_split_over_files_and_resume(nb, tmp_path, h5):
+    xd, md = nb.make_plummer_sphere(1500, M_total=1e9, a=1.0, seed=1)
+    xs, ms = nb.make_plummer_sphere(500, M_total=2e7, a=0.3, seed=2)
+    xv = np.vstack([xd, xs])
+    sp = [nb.Species.dark(1500, mass=float(md[0]), softening=0.05),
+          nb.Species.star(500, mass=float(ms[0]), softening=np.linspace(0.01, 0.03, 500))]
+    kw = dict(architecture="gpu", method="direct", verbose=False, snapshots=4, num_files_to_write=2)
+    full = nb.run_simulation(xv, sp, 0.0, 12e-4, 1e-4, output_dir=str(tmp_path / "full"), **kw)
+    f0, f1 = h5.flatten(tmp_path / "full" / "snapshot.000.h5"), h5.flatten(tmp_path / "full" / "snapshot.001.h5")
+    assert "/snapshots/snap.000" in f0 and "/snapshots/snap.001" in f0 and "/snapshots/snap.002" in f1 \
+        and "/snapshots/snap.003" in f1
+    assert [n.decode() for n in f0["/properties@species_names"]] == ["dark", "star"]
+    assert f0["/properties/star/eps_array"].shape == (500,) and float(f0["/properties/dark/eps"]) == 0.05
+    assert np.array_equal(f1["/snapshots/snap.003"], np.vstack([full["dark"], full["star"]]))
+    # stop after 8 of 12 steps, then continue_run: same snapshots, same final state
+    part = tmp_path / "part"
+    nb.run_simulation(xv, sp, 0.0, 8e-4, 1e-4, output_dir=str(part), **dict(kw, snapshots=3))   # steps 0, 4, 8
+    res = nb.run_simulation(xv, sp, 0.0, 12e-4, 1e-4, output_dir=str(part), continue_run=True, **kw)
+    assert np.array_equal(res["dark"], full["dark"]) and np.array_equal(res["star"], full["star"])
