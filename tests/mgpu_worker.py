@@ -81,6 +81,19 @@ def main():
     msgs.append(f"run float32_kahan vs float64: {e32:.2e}; diagnostics rows {len(diags)}")
     ok &= bool(e32 < 1e-4) and len(diags) == 3
 
+    # snapshots from a sharded run (rows gathered on every rank, rank 0 writes; HDF5 through the h5py stand-in)
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import fake_h5py
+
+    sys.modules["h5py"] = fake_h5py
+    sn = nb.run_nbody_gpu(xv, mass, 0.0, steps * dt, dt, h, output_dir=str(out / "snap"), snapshots=3,
+                          **dict(kw, save_snapshots=True))
+    dist.barrier()
+    flat = fake_h5py.flatten(out / "snap" / "snapshot.h5")
+    ok &= bool(np.array_equal(flat["/snapshots/snap.000"], xv)) and bool(np.array_equal(flat["/snapshots/snap.002"], sn))
+    ok &= bool(np.array_equal(sn, ovl)) and "/snapshots/snap.001" in flat
+    msgs.append(f"snapshots from a sharded run: 3 written, last equals the returned state {np.array_equal(flat['/snapshots/snap.002'], sn)}")
+
     # iterative unbinding with the target rows sharded over the ranks: masks identical on every rank and
     # equal to the single-GPU result
     from nbody_streams_b200.unbind import iterative_unbinding
