@@ -195,8 +195,8 @@ int nb_energy(const double *vel, const void *mass, int mass_dt,
 
 /* Select one of the compiled register-blocking variants of the plummer/spline
  * sweeps (f32: 0..3, f64: 0..2) or -1 = automatic, the default: the measured
- * best variant per (kernel, mode) — 0 except float64 spline (1) and float32
- * plummer force-only / potential-only (2).  NB_F32_VARIANT / NB_F64_VARIANT in the
+ * best variant per (kernel, mode) — 0 except float32 plummer force-only /
+ * potential-only (2).  NB_F32_VARIANT / NB_F64_VARIANT in the
  * environment set the initial value.  Changes nb_sweep_grid() results.
  * nb_get_variant returns the current setting (-1 for automatic). */
 int nb_set_variant(int prec, int variant);

@@ -59,10 +59,11 @@ int eff_variant(int prec, int kid, int mode) {
     const int v = prec == NB_PREC_F64 ? cur_variant_f64() : cur_variant_f32();
     if (v != VARIANT_AUTO) return v;
     // measured on B200 with this build (profiles/r01_variant_sweep.log): variant 0 everywhere except
-    //   float64 spline: 4 i per thread at 3 CTAs/SM, +3 % (more independent DFMA chains per warp)
     //   float32 plummer force-only / potential-only: 1 i-pair per thread at 8 CTAs/SM, +4.5 % / +4 %
-    //   (the fused force+potential loop needs the registers of the 2-pair blocking and stays on variant 0)
-    if (prec == NB_PREC_F64) return kid == NB_KERNEL_SPLINE ? 1 : 0;
+    //   (the fused force+potential loop needs the registers of the 2-pair blocking and stays on variant 0).
+    // float64: the three variants are within 2-3 % of each other and their order changes between builds
+    // (spline: variant 1 was +3 % before the division-free exact path, -2 % after) -> variant 0.
+    if (prec == NB_PREC_F64) return 0;
     return (kid == NB_KERNEL_PLUMMER && mode != NB_MODE_BOTH) ? 2 : 0;
 }
 int block_i_for(int prec, int kid, int mode) {
