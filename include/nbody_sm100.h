@@ -92,7 +92,9 @@ int nb_device_info(int *sm_count, int *cc_major, int *cc_minor,
  * the max of (max-softening rule, reference cuda_kernels.py:150).  c_uni / m_uni
  * are the common c / mass of the tile or NaN when its particles differ (tiles
  * with uniform values take faster sweep paths).
- * Padding particles (index >= n) have m = 0. */
+ * Padding particles (index >= n) have m = 0, c = 0 and are parked at x = y = z =
+ * 1e18 (f32) / 1e150 (f64), far from everything, so unmasked pair evaluations
+ * against them are finite and multiply a zero mass. */
 int    nb_tile_j(void);
 int    nb_block_i(int prec);                       /* i-particles per CTA work unit  */
 size_t nb_packed_bytes(int prec, long n);          /* bytes for n particles (padded) */
@@ -154,6 +156,60 @@ int nb_direct(int prec, int kernel_id, int mode,
               long n, double G, double eps2,
               void *packed, void *workspace, size_t workspace_bytes, int grid,
               void *acc, void *phi, void *stream);
+
+/* ---- the pair-symmetric O(N^2/2) sweep (large N) -------------------------- */
+
+/* The kernel factor of a pair, K(r_ij^2, max(h_i,h_j)), is symmetric in i and j
+ * (reference cuda_kernels.py:144-167 evaluates it once per ORDERED pair).  The
+ * symmetric sweep evaluates every unordered pair once and applies it to both
+ * particles: a_i += m_j K (r_j-r_i), a_j -= m_i K (r_j-r_i).  Work units are
+ * (i-block of nb_sym_block_tiles() tiles) x (j-tile); both sides' partial sums
+ * are added atomically, in double, into a workspace of 4 doubles per particle
+ * SLOT (ax, ay, az, s_phi), so results are reproducible to rounding of those
+ * double additions only (not bitwise; use nb_sweep for bitwise reproducibility).
+ * NB_PREC_F32 and NB_PREC_F32_COMP share one implementation here (float pair
+ * arithmetic, <= 256-term float partial sums, double above).
+ * nb_sym_min_n(): particle count from which callers should prefer this path
+ * (env NB_SYM_MIN_N, default 32768; below it the one-sided sweep's finer work
+ * units fill the GPU better). */
+long   nb_sym_min_n(void);
+int    nb_set_sym_min_n(long n);
+int    nb_sym_block_tiles(int prec);
+int    nb_sym_grid(int prec, int kernel_id, int mode, int *grid);
+size_t nb_sym_workspace_bytes(long n_slots);       /* 32 bytes per particle slot */
+
+/* One symmetric sweep for the i-tiles [it_begin, it_end) of `packed`:
+ *   tri != 0 : all pairs INSIDE the i-range (each once);
+ *   [ra_begin,ra_end) U [rb_begin,rb_end): j-tile ranges OUTSIDE the i-range,
+ *              swept by every i-block, results applied to both sides (other
+ *              ranks' shards in a multi-GPU run);
+ *   [rc_begin,rc_end): one more outside range, swept only by the i-blocks
+ *              [ibc_begin, ibc_end) (splits the opposite shard of an even ring).
+ * Tiles must exist in `packed` and hold real particles or nb_pack padding.
+ * Sums are ADDED into workspace rows of the particles' global slots
+ * (n_slots rows; zero_first != 0 clears all rows first, on the stream). */
+int nb_sym_sweep(int prec, int kernel_id, int mode,
+                 const void *packed, long n_j,
+                 int it_begin, int it_end, int tri,
+                 int ra_begin, int ra_end, int rb_begin, int rb_end,
+                 int rc_begin, int rc_end, int ibc_begin, int ibc_end,
+                 double eps2, void *workspace, size_t workspace_bytes,
+                 long n_slots, int zero_first, int grid, void *stream);
+
+/* acc (n_i,3) / phi (n_i) of the slots [first, first+n_i) from the workspace
+ * sums (x G; kernel dtype).  Either output may be NULL. */
+int nb_sym_finish(int prec, int mode, const void *workspace, long first, long n_i,
+                  double G, void *acc, void *phi, void *stream);
+
+/* pack + symmetric sweep of all pairs + finish; same arguments as nb_direct,
+ * workspace of nb_sym_workspace_bytes(nb_padded_count(n)), grid from nb_sym_grid. */
+int nb_direct_sym(int prec, int kernel_id, int mode,
+                  const void *pos, int pos_dt,
+                  const void *mass, int mass_dt, double mass_scalar,
+                  const void *h, int h_dt, double h_scalar,
+                  long n, double G, double eps2,
+                  void *packed, void *workspace, size_t workspace_bytes, int grid,
+                  void *acc, void *phi, void *stream);
 
 /* ---- fused KDK leapfrog pieces (reference run.py:666-695) ---------------- */
 

@@ -44,6 +44,16 @@ SIGNATURES = {
     "nb_finish": (_i, [_i, _i, _i, _l, _i, _i, C.POINTER(_i), _vp, _d, _vp, _vp, _vp]),
     "nb_direct": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _d, _vp, _i, _d, _l, _d, _d, _vp, _vp, _sz, _i, _vp, _vp,
                        _vp]),
+    "nb_sym_min_n": (_l, []),
+    "nb_set_sym_min_n": (_i, [_l]),
+    "nb_sym_block_tiles": (_i, [_i]),
+    "nb_sym_grid": (_i, [_i, _i, _i, C.POINTER(_i)]),
+    "nb_sym_workspace_bytes": (_sz, [_l]),
+    "nb_sym_sweep": (_i, [_i, _i, _i, _vp, _l, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _vp, _sz, _l, _i, _i,
+                          _vp]),
+    "nb_sym_finish": (_i, [_i, _i, _vp, _l, _l, _d, _vp, _vp, _vp]),
+    "nb_direct_sym": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _d, _vp, _i, _d, _l, _d, _d, _vp, _vp, _sz, _i, _vp, _vp,
+                           _vp]),
     "nb_kick_drift_pack": (_i, [_i, _vp, _vp, _vp, _i, _vp, _vp, _l, _l, _d, _d, _vp]),
     "nb_kick_drift_push": (_i, [_i, _vp, _vp, _vp, _i, _vp, C.POINTER(_vp), _i, _vp, _l, _l, _d, _d, _vp]),
     "nb_kick": (_i, [_vp, _vp, _i, _vp, _l, _d, _vp]),

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "nb_dispatch.cuh"
+#include "nb_sym_dispatch.cuh"
 
 // launchers defined in nb_misc.cu / nb_ubench.cu
 int nb_launch_pack(int prec, int kernel_id, void* packed, long long first, const void* pos, int pos_dt,
@@ -11,6 +12,8 @@ int nb_launch_pack(int prec, int kernel_id, void* packed, long long first, const
                    long long n, long long n_pad, double eps2, cudaStream_t st);
 int nb_launch_finish(int prec, long long n_i, int grid, int IB, int n_sweeps, const int* n_jt, const void* ws,
                      size_t slot_bytes, size_t part_off, double G, void* acc, void* phi, cudaStream_t st);
+int nb_launch_sym_finish(int prec, const void* ws, long long first, long long n_i, double G, void* acc, void* phi,
+                         cudaStream_t st);
 int nb_launch_kick_drift_pack(int prec, double* pos, double* vel, const void* acc, int acc_dt,
                               const double* acc_ext, void* packed, long long first, long long n, double dt_half,
                               double dt, cudaStream_t st);
@@ -103,6 +106,21 @@ int dispatch(int prec, int kid, int mode, int op, const SweepArgs* a, int grid, 
     }
     return NB_E_INVALID_ARG;
 }
+
+int dispatch_sym(int prec, int kid, int mode, int op, const SymArgs* a, int grid, int* out, cudaStream_t st) {
+    switch (kid) {
+        case 0: return nb_dispatch_sym_k0(prec, mode, op, a, grid, out, st);
+        case 1: return nb_dispatch_sym_k1(prec, mode, op, a, grid, out, st);
+        case 2: return nb_dispatch_sym_k2(prec, mode, op, a, grid, out, st);
+        case 3: return nb_dispatch_sym_k3(prec, mode, op, a, grid, out, st);
+        case 4: return nb_dispatch_sym_k4(prec, mode, op, a, grid, out, st);
+    }
+    return NB_E_INVALID_ARG;
+}
+int sym_tpb(int prec) { return prec == NB_PREC_F64 ? SYM_TPB_F64 : SYM_TPB_F32; }
+
+constexpr long SYM_MIN_N_DEFAULT = 32768;   // below this the one-sided sweep's finer work units win
+long g_sym_min_n = -1;
 
 struct SlotLayout {
     size_t full_bytes, part_off, slot_bytes;
@@ -284,6 +302,106 @@ int nb_direct(int prec, int kernel_id, int mode, const void* pos, int pos_dt, co
                   grid, stream);
     if (rc) return rc;
     return nb_finish(prec, kernel_id, mode, n, grid, 1, &n_tiles, workspace, G, acc, phi, stream);
+}
+
+/* ---- pair-symmetric sweeps ------------------------------------------------ */
+
+long nb_sym_min_n(void) {
+    if (g_sym_min_n < 0) {
+        const char* s = std::getenv("NB_SYM_MIN_N");
+        g_sym_min_n = (s && *s) ? std::atol(s) : SYM_MIN_N_DEFAULT;
+        if (g_sym_min_n < 0) g_sym_min_n = 0;
+    }
+    return g_sym_min_n;
+}
+int nb_set_sym_min_n(long n) {
+    if (n < 0) return NB_E_INVALID_ARG;
+    g_sym_min_n = n;
+    return 0;
+}
+int nb_sym_block_tiles(int prec) { return valid_prec(prec) ? sym_tpb(prec) : 0; }
+
+int nb_sym_grid(int prec, int kernel_id, int mode, int* grid) {
+    if (!valid_prec(prec) || !valid_kid(kernel_id) || !valid_mode(mode) || !grid) return NB_E_INVALID_ARG;
+    int dev = 0, sms = 0, major = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return NB_E_ARCH;
+    int per_sm = 0;
+    const int rc = dispatch_sym(prec, kernel_id, mode, SYM_OP_QUERY, nullptr, 0, &per_sm, 0);
+    if (rc) return rc;
+    if (per_sm < 1) per_sm = 1;
+    *grid = sms * per_sm;
+    return 0;
+}
+
+size_t nb_sym_workspace_bytes(long n_slots) { return n_slots > 0 ? static_cast<size_t>(n_slots) * 32 : 0; }
+
+int nb_sym_sweep(int prec, int kernel_id, int mode, const void* packed, long n_j, int it_begin, int it_end, int tri,
+                 int ra_begin, int ra_end, int rb_begin, int rb_end, int rc_begin, int rc_end, int ibc_begin,
+                 int ibc_end, double eps2, void* workspace, size_t workspace_bytes, long n_slots, int zero_first,
+                 int grid, void* stream) {
+    if (!valid_prec(prec) || !valid_kid(kernel_id) || !valid_mode(mode)) return NB_E_INVALID_ARG;
+    if (!packed || !workspace || n_j < 0 || grid <= 0 || n_slots < 0) return NB_E_INVALID_ARG;
+    if (it_begin < 0 || it_end < it_begin || ra_begin < 0 || ra_end < ra_begin || rb_begin < 0 || rb_end < rb_begin ||
+        rc_begin < 0 || rc_end < rc_begin || ibc_begin < 0 || ibc_end < ibc_begin)
+        return NB_E_INVALID_ARG;
+    if (workspace_bytes < nb_sym_workspace_bytes(n_slots)) return NB_E_WORKSPACE;
+    // every tile touched must have workspace rows; tiles must hold real particles or sentinel padding
+    const long max_tile = n_slots / TJ;
+    if (it_end > max_tile || ra_end > max_tile || rb_end > max_tile || rc_end > max_tile) return NB_E_INVALID_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (zero_first) {
+        cudaError_t e = cudaMemsetAsync(workspace, 0, nb_sym_workspace_bytes(n_slots), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int TPB = sym_tpb(prec);
+    SymArgs a;
+    a.packed = static_cast<const unsigned char*>(packed);
+    a.n_j  = n_j;
+    a.it0  = it_begin;
+    a.nT   = it_end - it_begin;
+    a.n_ib = (a.nT + TPB - 1) / TPB;
+    a.tri  = tri ? 1 : 0;
+    a.rA0 = ra_begin; a.lenA = ra_end - ra_begin;
+    a.rB0 = rb_begin; a.lenB = rb_end - rb_begin;
+    a.rC0 = rc_begin; a.lenC = rc_end - rc_begin;
+    a.ibC0 = ibc_begin < a.n_ib ? ibc_begin : a.n_ib;
+    a.ibC1 = ibc_end < a.n_ib ? ibc_end : a.n_ib;
+    if (a.ibC1 < a.ibC0) a.ibC1 = a.ibC0;
+    a.eps2 = eps2;
+    a.ws   = static_cast<double*>(workspace);
+    if (a.n_ib == 0) return 0;
+    a.total = prec == NB_PREC_F64 ? sym_prefix<SYM_TPB_F64>(a, a.n_ib) : sym_prefix<SYM_TPB_F32>(a, a.n_ib);
+    if (a.total <= 0) return 0;
+    return dispatch_sym(prec, kernel_id, mode, SYM_OP_LAUNCH, &a, grid, nullptr, st);
+}
+
+int nb_sym_finish(int prec, int mode, const void* workspace, long first, long n_i, double G, void* acc, void* phi,
+                  void* stream) {
+    if (!valid_prec(prec) || !valid_mode(mode) || !workspace || first < 0 || n_i < 0) return NB_E_INVALID_ARG;
+    if (!(mode & NB_MODE_FORCE)) acc = nullptr;
+    if (!(mode & NB_MODE_POT)) phi = nullptr;
+    return nb_launch_sym_finish(prec, workspace, first, n_i, G, acc, phi, static_cast<cudaStream_t>(stream));
+}
+
+int nb_direct_sym(int prec, int kernel_id, int mode, const void* pos, int pos_dt, const void* mass, int mass_dt,
+                  double mass_scalar, const void* h, int h_dt, double h_scalar, long n, double G, double eps2,
+                  void* packed, void* workspace, size_t workspace_bytes, int grid, void* acc, void* phi,
+                  void* stream) {
+    if (n < 0) return NB_E_INVALID_ARG;
+    if (n == 0) return 0;
+    const long n_pad = nb_padded_count(n);
+    int rc = nb_pack(prec, kernel_id, packed, 0, pos, pos_dt, mass, mass_dt, mass_scalar, h, h_dt, h_scalar, n,
+                     n_pad, eps2, stream);
+    if (rc) return rc;
+    const int n_tiles = static_cast<int>(n_pad / TJ);
+    rc = nb_sym_sweep(prec, kernel_id, mode, packed, n, 0, n_tiles, 1, 0, 0, 0, 0, 0, 0, 0, 0, eps2, workspace,
+                      workspace_bytes, n_pad, 1, grid, stream);
+    if (rc) return rc;
+    return nb_sym_finish(prec, mode, workspace, 0, n, G, acc, phi, stream);
 }
 
 int nb_kick_drift_pack(int prec, double* pos, double* vel, const void* acc, int acc_dt, const double* acc_ext,

@@ -35,6 +35,12 @@ constexpr int TILE_BYTES_F32 = TJ * 20 + TILE_META_BYTES;
 constexpr int TILE_BYTES_F64 = TJ * 40 + TILE_META_BYTES;
 constexpr int COMP_X = 0, COMP_Y = 1, COMP_Z = 2, COMP_M = 3, COMP_C = 4;
 
+// Padding records (index >= n) and dummy i-particles: zero mass, zero softening and a position far away
+// from everything, so that an unmasked pair with a real particle evaluates to finite values times m = 0
+// (r^2 ~ 3e36 / 3e300 stays inside the exponent range; a pad sitting ON a real particle would give inf * 0).
+constexpr float NB_PAD_POS_F32  = 1.0e18f;
+constexpr double NB_PAD_POS_F64 = 1.0e150;
+
 // ---------------------------------------------------------------------------
 // PTX: mbarrier + 1-D bulk async copy (TMA engine; SASS UBLKCP / SYNCS)
 // ---------------------------------------------------------------------------
@@ -141,39 +147,11 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
 
 // ---------------------------------------------------------------------------
 // Cubic-spline (Monaghan 1992) pieces, evaluated only for pairs with r < h.
-// Restates cuda_kernels.py:61-87 (force) and :405-436 (potential); T = float
-// or double.  Returns the 1/r^3-equivalent factor w and the -1/r-equivalent phi.
+// Restates cuda_kernels.py:61-87 (force) and :405-436 (potential); T = float or double.
 // ---------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ T spline_w_inside(T r, T h) {
-    const T hinv  = T(1) / h;
-    const T q     = r * hinv;
-    const T h3inv = hinv * hinv * hinv;
-    if (q < T(1e-8)) return h3inv * T(10.666666666666666);
-    const T q2 = q * q;
-    if (q <= T(0.5)) return h3inv * (T(10.666666666666666) + q2 * (T(32.0) * q - T(38.4)));
-    const T q3 = q2 * q;
-    return h3inv * (T(21.333333333333333) + q * (T(-48.0) + q * (T(38.4) - T(10.666666666666667) * q)) -
-                    T(0.06666666666666667) / q3);
-}
-template <typename T>
-__device__ __forceinline__ T spline_phi_inside(T r, T h) {
-    const T hinv = T(1) / h;
-    const T q    = r * hinv;
-    if (q < T(1e-8)) return T(-2.8) * hinv;
-    const T q2 = q * q;
-    if (q <= T(0.5)) {
-        const T q4 = q2 * q2;
-        return (T(-2.8) + q2 * (T(5.333333333333333) + q4 * (T(6.4) * q - T(9.6)))) * hinv;
-    }
-    return (T(-3.2) + T(0.06666666666666667) / q +
-            q2 * (T(10.666666666666666) + q * (T(-16.0) + q * (T(9.6) - T(2.1333333333333333) * q)))) *
-           hinv;
-}
-
-// Division-free form of the two functions above for the sweeps' exact paths: given d = r^2 (> 0 or 0),
-// rinv = 1/r and hinv = 1/h (both from the kernels' reciprocal square roots) it returns w (the
-// 1/r^3-equivalent) and p (the +1/r-equivalent, i.e. minus spline_phi_inside).  Same polynomials; the
+// Division-free form for the sweeps' exact paths: given d = r^2 (> 0 or 0), rinv = 1/r and hinv = 1/h
+// (both from the kernels' reciprocal square roots) it returns w (the 1/r^3-equivalent force factor) and p
+// (the +1/r-equivalent, i.e. minus the potential factor).  The reference's polynomials in q = r/h; its
 // -(1/15)/q^3 and (1/15)/q terms of the outer branch are written as (1/15) rinv^3 and (1/15) rinv.
 // d == 0 (coincident particles with eps2 = 0) takes the q -> 0 limit like the reference's q < 1e-8 case.
 template <typename T>

@@ -7,6 +7,7 @@
 // run.py:188,195 (dtype casts), run.py:672,675,695 (kick / drift),
 // run.py:619-623 (energies).
 #include "nb_sweep.cuh"
+#include "nb_sym.cuh"
 
 namespace nb {
 
@@ -28,7 +29,9 @@ __global__ void __launch_bounds__(TJ) pack_kernel(unsigned char* __restrict__ ti
     const int k       = threadIdx.x;
     const long long idx = t * TJ + k;
     T* tb = reinterpret_cast<T*>(tiles + static_cast<size_t>(t) * TB);
-    T x = T(0), y = T(0), z = T(0), m = T(0), c = T(0);   // padding: zero mass, zero softening
+    // padding: zero mass, zero softening, parked far away (see NB_PAD_POS_*)
+    const T pad = (sizeof(T) == 8) ? static_cast<T>(NB_PAD_POS_F64) : static_cast<T>(NB_PAD_POS_F32);
+    T x = pad, y = pad, z = pad, m = T(0), c = T(0);
     if (idx < n) {
         // cast to the kernel dtype FIRST (reference: pos.astype(dtype), run.py:188), then square h
         x = static_cast<T>(load_as_double(pos, pos_dt, 3 * idx + 0));
@@ -142,6 +145,21 @@ __global__ void finish_kernel(const FinishArgs a, OT* __restrict__ acc, OT* __re
         acc[3 * i + 2] = static_cast<OT>(a.G * sz);
     }
     if (phi) phi[i] = static_cast<OT>(-a.G * sp);
+}
+
+// finish of the pair-symmetric sweeps: the workspace already holds the complete double sums of every slot
+template <typename OT>
+__global__ void sym_finish_kernel(const double4* __restrict__ ws, long long first, long long n_i, double G,
+                                  OT* __restrict__ acc, OT* __restrict__ phi) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_i) return;
+    const double4 v = ws[first + i];
+    if (acc) {
+        acc[3 * i + 0] = static_cast<OT>(G * v.x);
+        acc[3 * i + 1] = static_cast<OT>(G * v.y);
+        acc[3 * i + 2] = static_cast<OT>(G * v.z);
+    }
+    if (phi) phi[i] = static_cast<OT>(-G * v.w);
 }
 
 // ---------------------------------------------------------------------------
@@ -353,6 +371,22 @@ int nb_launch_finish(int prec, long long n_i, int grid, int IB, int n_sweeps, co
                                                                    static_cast<double*>(phi));
     else
         finish_kernel<double4, float><<<blocks, threads, 0, st>>>(a, static_cast<float*>(acc), static_cast<float*>(phi));
+    NB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int nb_launch_sym_finish(int prec, const void* ws, long long first, long long n_i, double G, void* acc, void* phi,
+                         cudaStream_t st) {
+    if (n_i <= 0) return 0;
+    const int threads = n_i >= 148 * 256 ? 256 : 64;
+    const unsigned blocks = static_cast<unsigned>((n_i + threads - 1) / threads);
+    const double4* w = static_cast<const double4*>(ws);
+    if (prec == NB_PREC_F64)
+        sym_finish_kernel<double><<<blocks, threads, 0, st>>>(w, first, n_i, G, static_cast<double*>(acc),
+                                                              static_cast<double*>(phi));
+    else
+        sym_finish_kernel<float><<<blocks, threads, 0, st>>>(w, first, n_i, G, static_cast<float*>(acc),
+                                                             static_cast<float*>(phi));
     NB_CUDA_OK(cudaGetLastError());
     return 0;
 }

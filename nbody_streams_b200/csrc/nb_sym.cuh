@@ -1,0 +1,81 @@
+// nb_sym.cuh — argument block + work-unit enumeration of the PAIR-SYMMETRIC sweeps.
+//
+// The one-sided sweeps (nb_sweep_f32.cuh / nb_sweep_f64.cuh) evaluate every ordered pair (i, j): N^2 kernel
+// evaluations, like the reference kernels (cuda_kernels.py:141-168).  The kernel factor of a pair,
+// K(r_ij^2, max(h_i, h_j)), is symmetric in i and j, so the symmetric sweeps evaluate every UNORDERED pair
+// once and apply it to both particles (Newton's third law): a_i += m_j K (r_j - r_i), a_j -= m_i K (r_j - r_i).
+// Per pair that is 3 more FMAs but no second distance / rsqrt / kernel evaluation: 14 instead of 2 x 11
+// packed FP32 instructions per two interactions.
+//
+// Work decomposition: i-blocks of TPB tiles (the particles a CTA keeps in registers) x j-tiles.  For an i-range
+// of tiles [it0, it0+nT) a block ib sweeps
+//     - (tri) the tiles of its own range from its first tile on: the first TPB of them overlap the block itself
+//       ("diagonal": one-sided masked path, self pairs excluded), the rest are symmetric;
+//     - the rectangle ranges A and B (other ranks' shards, symmetric);
+//     - range C if ibC0 <= ib < ibC1 (the half-shard rule that splits the opposite shard of an even ring).
+// Units are linearised block-major and cut into equal contiguous pieces per CTA (stream-K); partial sums of
+// both sides are added atomically (double) into ws[slot][4], so pieces need no fix-up pass.
+#pragma once
+#include "nb_common.cuh"
+
+namespace nb {
+
+struct SymArgs {
+    const unsigned char* packed;  // tile-major particle records
+    long long n_j;                // real particles in `packed` (index >= n_j is padding)
+    int it0, nT;                  // i-range: tiles [it0, it0 + nT)
+    int n_ib;                     // i-blocks = ceil(nT / TPB)
+    int tri;                      // sweep the triangle inside the i-range
+    int rA0, lenA, rB0, lenB;     // rectangle j-tile ranges (every i-block)
+    int rC0, lenC, ibC0, ibC1;    // extra range for i-blocks [ibC0, ibC1)
+    long long total;              // work units
+    double eps2;
+    double* ws;                   // [slots][4] doubles: sum of ax, ay, az, s_phi (atomically accumulated)
+};
+
+// units of the i-blocks before ib
+template <int TPB>
+__host__ __device__ inline long long sym_prefix(const SymArgs& a, long long ib) {
+    long long p = ib * static_cast<long long>(a.lenA + a.lenB);
+    if (a.tri) p += ib * a.nT - static_cast<long long>(TPB) * (ib * (ib - 1) / 2);
+    long long c = ib - a.ibC0;
+    const long long cmax = a.ibC1 - a.ibC0;
+    if (c > cmax) c = cmax;
+    if (c > 0) p += c * a.lenC;
+    return p;
+}
+template <int TPB>
+__host__ __device__ inline int sym_count(const SymArgs& a, int ib) {
+    int n = a.lenA + a.lenB;
+    if (a.tri) n += a.nT - TPB * ib;
+    if (ib >= a.ibC0 && ib < a.ibC1) n += a.lenC;
+    return n;
+}
+// the i-block holding unit u: largest ib with prefix(ib) <= u
+template <int TPB>
+__host__ __device__ inline int sym_find_block(const SymArgs& a, long long u) {
+    int lo = 0, hi = a.n_ib - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (sym_prefix<TPB>(a, mid) <= u) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+// global tile of local unit jl of block ib; diag = the tile overlaps the block's own particles
+template <int TPB>
+__host__ __device__ inline int sym_tile(const SymArgs& a, int ib, int jl, bool& diag) {
+    const int triA = a.tri ? a.nT - TPB * ib : 0;
+    if (jl < triA) {
+        diag = jl < TPB;
+        return a.it0 + TPB * ib + jl;
+    }
+    diag = false;
+    jl -= triA;
+    if (jl < a.lenA) return a.rA0 + jl;
+    jl -= a.lenA;
+    if (jl < a.lenB) return a.rB0 + jl;
+    return a.rC0 + (jl - a.lenB);
+}
+
+}  // namespace nb

@@ -1,0 +1,545 @@
+// nb_sym_f32.cuh — pair-symmetric FP32 sweep (NB_PREC_F32 / NB_PREC_F32_COMP), the large-N path.
+//
+// Same job as nb_sweep_f32.cuh (replaces nbody_forces_kernel_float4 / ..._kahan_kernel_float4 /
+// nbody_potential_kernel_float4 / ..._kahan..., reference cuda_kernels.py:90-179, :254-366, :439-518,
+// :591-677) but every unordered pair is evaluated ONCE and applied to both particles (see nb_sym.cuh).
+//
+// Data flow inside a CTA (128 threads = 4 warps, one (i-block x j-tile) unit at a time):
+//   * i side: each thread owns NP = 4 packed pairs of i-particles (8 i, 1024 per CTA) in 64-bit registers,
+//     exactly like the one-sided sweep; partial sums over one tile are folded into float running sums in
+//     shared memory and those are added to the double workspace every SYM_FLUSH_TILES tiles (blocked
+//     summation: 256-term float partials, 8-term float second level, double above that);
+//   * j side: the tile (TMA bulk copy into the ring) is processed in rounds of 32 j-particles, ONE PER LANE.
+//     In step s of a round lane l works on particle (l + s) mod 32: it reads that particle's record with a
+//     conflict-free LDS, evaluates it against its 8 i-particles with packed FADD2/FFMA2/FMUL2, accumulates
+//     +K dx into its own a_i and into the particle's travelling accumulator, and hands that accumulator to
+//     lane l-1 with SHFL (a systolic rotation).  After 32 steps every particle has met all 256 i-particles of
+//     the warp and its accumulator is back in lane (j mod 32), which stores it to the warp's slice of a
+//     shared buffer.  After the tile the four slices are added in double and added atomically to ws.
+//   * tiles that overlap the CTA's own i-block ("diagonal") run the one-sided masked path of
+//     nb_sweep_f32.cuh (self pairs excluded) and contribute to the i side only.
+// Bound: FP32 pipe, 14 (force) / 16 (force+potential) packed instructions + 2 MUFU per 128 interactions.
+#pragma once
+#include "nb_sweep_f32.cuh"
+#include "nb_sym.cuh"
+
+namespace nb {
+
+constexpr int SYM_NP          = 4;                       // packed i-pairs per thread
+constexpr int SYM_IB_F32      = THREADS * 2 * SYM_NP;    // 1024 i-particles per CTA
+constexpr int SYM_TPB_F32     = SYM_IB_F32 / TJ;         // 4 tiles per i-block
+constexpr int SYM_FLUSH_TILES = 8;                       // i-side: float running sums -> double workspace
+
+__device__ __forceinline__ f2 shfl2(const f2 v, const int src) {
+    float lo, hi;
+    upk(v, lo, hi);
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    return pk(lo, hi);
+}
+__device__ __forceinline__ float sum2(const f2 v) {
+    float lo, hi;
+    upk(v, lo, hi);
+    return lo + hi;
+}
+
+// the travelling accumulators of one j-particle: packed (contributions of the even i, of the odd i)
+struct JAcc32 {
+    f2 x, y, z, p;
+};
+
+// ---------------------------------------------------------------------------
+// one (pair of i) x (one j) evaluation applied to both sides.
+//   U = true : i-block and j-tile have uniform mass and softening -> sums are unweighted (the masses are
+//              applied when the sums are folded / flushed) and cc = softening term of the pair
+//   U = false: general path, per-particle masses and max-softening rule per pair
+// ---------------------------------------------------------------------------
+template <int KID, int MODE, bool U>
+__device__ __forceinline__ void sym_pair_f32(const float xj, const float yj, const float zj, const float mj,
+                                             const float cj, const f2 xi, const f2 yi, const f2 zi, const f2 mi,
+                                             const float ci0, const float ci1, const f2 cc, f2& ax, f2& ay, f2& az,
+                                             f2& sp, JAcc32& J, const float eps2) {
+    const f2 dx = sub2(splat(xj), xi);
+    const f2 dy = sub2(splat(yj), yi);
+    const f2 dz = sub2(splat(zj), zi);
+    constexpr bool kUsesC = (KID == NB_KERNEL_PLUMMER || KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
+    constexpr bool kDehnen = (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
+    f2 h2, c;
+    if (KID == NB_KERNEL_NEWTONIAN) {
+        h2 = c = splat(eps2);
+    } else {
+        h2 = U ? cc : pk(fmaxf(cj, ci0), fmaxf(cj, ci1));
+        c  = kUsesC ? h2 : splat(eps2);
+    }
+    const f2 d = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, c)));
+    float d0, d1;
+    upk(d, d0, d1);
+    const f2 rinv  = pk(rsqrt_approx(d0), rsqrt_approx(d1));
+    const f2 rinv2 = mul2(rinv, rinv);
+    f2 w = 0ull, p = rinv;   // mass-less force factor (1/r^3-like) and potential factor (1/r-like)
+    if (kDehnen) {
+        const f2 t = mul2(add2(h2, splat(-eps2)), rinv2);   // c = h^2 + eps2 seeds the chain; the terms use bare h^2
+        if (MODE & NB_MODE_POT) {
+            const f2 pf = (KID == NB_KERNEL_DEHNEN_K1) ? fma2(splat(0.5f), t, splat(1.f))
+                                                       : fma2(t, fma2(splat(0.375f), t, splat(0.5f)), splat(1.f));
+            p = mul2(rinv, pf);
+        }
+        if (MODE & NB_MODE_FORCE) {
+            const f2 ff = (KID == NB_KERNEL_DEHNEN_K1) ? fma2(splat(1.5f), t, splat(1.f))
+                                                       : fma2(t, fma2(splat(3.75f), t, splat(1.5f)), splat(1.f));
+            w = mul2(mul2(rinv, rinv2), ff);
+        }
+    } else if (MODE & NB_MODE_FORCE) {
+        w = mul2(rinv, rinv2);
+    }
+    if (U) {
+        if (MODE & NB_MODE_POT) {
+            sp  = add2(sp, p);
+            J.p = add2(J.p, p);
+        }
+        if (MODE & NB_MODE_FORCE) {
+            ax  = fma2(w, dx, ax);
+            ay  = fma2(w, dy, ay);
+            az  = fma2(w, dz, az);
+            J.x = fma2(w, dx, J.x);
+            J.y = fma2(w, dy, J.y);
+            J.z = fma2(w, dz, J.z);
+        }
+    } else {
+        const f2 mjs = splat(mj);
+        if (MODE & NB_MODE_POT) {
+            sp  = fma2(mjs, p, sp);
+            J.p = fma2(mi, p, J.p);
+        }
+        if (MODE & NB_MODE_FORCE) {
+            const f2 fi = mul2(mjs, w), fj = mul2(mi, w);
+            ax  = fma2(fi, dx, ax);
+            ay  = fma2(fi, dy, ay);
+            az  = fma2(fi, dz, az);
+            J.x = fma2(fj, dx, J.x);
+            J.y = fma2(fj, dy, J.y);
+            J.z = fma2(fj, dz, J.z);
+        }
+    }
+}
+
+// exact cubic-spline evaluation of one scalar pair, both sides (the rare r < h case; reference
+// cuda_kernels.py:61-87 / :405-436 restated in spline_inside)
+template <int MODE>
+__device__ __forceinline__ void sym_spline_exact(const float xj, const float yj, const float zj, const float mj,
+                                                 const float cj, const float xi, const float yi, const float zi,
+                                                 const float mi, const float ci, float& ax, float& ay, float& az,
+                                                 float& sp, float& jx, float& jy, float& jz, float& jp,
+                                                 const float eps2) {
+    const float dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    const float d  = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, eps2)));
+    const float h2 = fmaxf(cj, ci);
+    float w, p;
+    const float ri = rsqrt_approx(d);
+    if (d < h2) {
+        spline_inside<float>(d, ri, rsqrt_approx(h2), w, p);
+    } else {
+        p = ri;
+        w = ri * (ri * ri);
+    }
+    if (MODE & NB_MODE_FORCE) {
+        const float fi = mj * w, fj = mi * w;
+        ax = fmaf(fi, dx, ax);
+        ay = fmaf(fi, dy, ay);
+        az = fmaf(fi, dz, az);
+        jx = fmaf(fj, dx, jx);
+        jy = fmaf(fj, dy, jy);
+        jz = fmaf(fj, dz, jz);
+    }
+    if (MODE & NB_MODE_POT) {
+        sp = fmaf(mj, p, sp);
+        jp = fmaf(mi, p, jp);
+    }
+}
+
+// thread state handed to the non-inlined cold paths (kept out of the hot loop's register allocation)
+template <int NP>
+struct SymCold32 {
+    IState<NP> S;
+    f2 m[NP];
+    JAcc32 J;
+};
+
+// the whole step (NP i-pairs x this lane's j) with the exact spline; U: unweighted sums
+template <int MODE, bool U, int NP>
+__device__ __noinline__ void sym_spline_exact_step(SymCold32<NP>* T, const float xj, const float yj, const float zj,
+                                                   const float mj_in, const float cj, const float eps2) {
+    float jx0, jx1, jy0, jy1, jz0, jz1, jp0, jp1;
+    upk(T->J.x, jx0, jx1); upk(T->J.y, jy0, jy1); upk(T->J.z, jz0, jz1); upk(T->J.p, jp0, jp1);
+    const float mj = U ? 1.f : mj_in;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        float x0, x1, y0, y1, z0, z1, m0, m1, ax0, ax1, ay0, ay1, az0, az1, sp0, sp1;
+        upk(T->S.x[q], x0, x1); upk(T->S.y[q], y0, y1); upk(T->S.z[q], z0, z1);
+        upk(T->S.ax[q], ax0, ax1); upk(T->S.ay[q], ay0, ay1); upk(T->S.az[q], az0, az1); upk(T->S.sp[q], sp0, sp1);
+        upk(T->m[q], m0, m1);
+        if (U) m0 = m1 = 1.f;
+        sym_spline_exact<MODE>(xj, yj, zj, mj, cj, x0, y0, z0, m0, T->S.c0[q], ax0, ay0, az0, sp0, jx0, jy0, jz0, jp0, eps2);
+        sym_spline_exact<MODE>(xj, yj, zj, mj, cj, x1, y1, z1, m1, T->S.c1[q], ax1, ay1, az1, sp1, jx1, jy1, jz1, jp1, eps2);
+        T->S.ax[q] = pk(ax0, ax1); T->S.ay[q] = pk(ay0, ay1); T->S.az[q] = pk(az0, az1); T->S.sp[q] = pk(sp0, sp1);
+    }
+    T->J.x = pk(jx0, jx1); T->J.y = pk(jy0, jy1); T->J.z = pk(jz0, jz1); T->J.p = pk(jp0, jp1);
+}
+
+// ---------------------------------------------------------------------------
+// one symmetric j-tile against this thread's NP pairs; jw = this warp's slice [4][TJ] of the j-side buffer
+// ---------------------------------------------------------------------------
+template <int KID, int MODE, bool U, int NP>
+__device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ stage, IState<NP>& S,
+                                             const f2 (&mi)[NP], const float cmax_i, const float c_pair,
+                                             const float eps2, float* __restrict__ jw, const int lane) {
+    const float* __restrict__ sX = reinterpret_cast<const float*>(stage) + COMP_X * TJ;
+    const float* __restrict__ sY = reinterpret_cast<const float*>(stage) + COMP_Y * TJ;
+    const float* __restrict__ sZ = reinterpret_cast<const float*>(stage) + COMP_Z * TJ;
+    const float* __restrict__ sM = reinterpret_cast<const float*>(stage) + COMP_M * TJ;
+    const float* __restrict__ sC = reinterpret_cast<const float*>(stage) + COMP_C * TJ;
+    const f2 cc   = splat(c_pair);
+    const f2 ceps = splat(eps2);
+    const int src = (lane + 1) & 31;
+
+#pragma unroll 1
+    for (int rho = 0; rho < TJ / 32; ++rho) {
+        JAcc32 J;
+        J.x = J.y = J.z = J.p = 0ull;
+        const int jb = 32 * rho;
+#pragma unroll 2
+        for (int s = 0; s < 32; ++s) {
+            const int jj   = jb + ((lane + s) & 31);
+            const float xj = sX[jj], yj = sY[jj], zj = sZ[jj];
+            float mj = 1.f, cj = c_pair;
+            if (!U) {
+                mj = sM[jj];
+                cj = sC[jj];
+            }
+            if (KID != NB_KERNEL_SPLINE) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q)
+                    sym_pair_f32<KID, MODE, U>(xj, yj, zj, mj, cj, S.x[q], S.y[q], S.z[q], mi[q], S.c0[q], S.c1[q], cc,
+                                               S.ax[q], S.ay[q], S.az[q], S.sp[q], J, eps2);
+            } else {
+                // two-phase: separations + r^2 and their minimum first; Newtonian finish unless some pair of
+                // the step may lie inside its softening length (then the step is redone exactly)
+                f2 dx[NP], dy[NP], dz[NP], d[NP];
+                float dmin = 3.0e38f;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    dx[q] = sub2(splat(xj), S.x[q]);
+                    dy[q] = sub2(splat(yj), S.y[q]);
+                    dz[q] = sub2(splat(zj), S.z[q]);
+                    d[q]  = fma2(dx[q], dx[q], fma2(dy[q], dy[q], fma2(dz[q], dz[q], ceps)));
+                    float d0, d1;
+                    upk(d[q], d0, d1);
+                    dmin = fminf(dmin, fminf(d0, d1));
+                }
+                const float h2lim = U ? c_pair : fmaxf(cj, cmax_i);
+                if (dmin < h2lim) {
+                    SymCold32<NP> T;
+                    T.S = S;
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) T.m[q] = mi[q];
+                    T.J = J;
+                    sym_spline_exact_step<MODE, U, NP>(&T, xj, yj, zj, mj, cj, eps2);
+                    S = T.S;
+                    J = T.J;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        float d0, d1;
+                        upk(d[q], d0, d1);
+                        const f2 rinv = pk(rsqrt_approx(d0), rsqrt_approx(d1));
+                        if (U) {
+                            if (MODE & NB_MODE_POT) {
+                                S.sp[q] = add2(S.sp[q], rinv);
+                                J.p     = add2(J.p, rinv);
+                            }
+                            if (MODE & NB_MODE_FORCE) {
+                                const f2 w = mul2(rinv, mul2(rinv, rinv));
+                                S.ax[q] = fma2(w, dx[q], S.ax[q]);
+                                S.ay[q] = fma2(w, dy[q], S.ay[q]);
+                                S.az[q] = fma2(w, dz[q], S.az[q]);
+                                J.x     = fma2(w, dx[q], J.x);
+                                J.y     = fma2(w, dy[q], J.y);
+                                J.z     = fma2(w, dz[q], J.z);
+                            }
+                        } else {
+                            const f2 mjs = splat(mj);
+                            if (MODE & NB_MODE_POT) {
+                                S.sp[q] = fma2(mjs, rinv, S.sp[q]);
+                                J.p     = fma2(mi[q], rinv, J.p);
+                            }
+                            if (MODE & NB_MODE_FORCE) {
+                                const f2 w  = mul2(rinv, mul2(rinv, rinv));
+                                const f2 fi = mul2(mjs, w), fj = mul2(mi[q], w);
+                                S.ax[q] = fma2(fi, dx[q], S.ax[q]);
+                                S.ay[q] = fma2(fi, dy[q], S.ay[q]);
+                                S.az[q] = fma2(fi, dz[q], S.az[q]);
+                                J.x     = fma2(fj, dx[q], J.x);
+                                J.y     = fma2(fj, dy[q], J.y);
+                                J.z     = fma2(fj, dz[q], J.z);
+                            }
+                        }
+                    }
+                }
+            }
+            // systolic rotation: the accumulators follow their j-particle to the lane that meets it next
+            if (MODE & NB_MODE_FORCE) {
+                J.x = shfl2(J.x, src);
+                J.y = shfl2(J.y, src);
+                J.z = shfl2(J.z, src);
+            }
+            if (MODE & NB_MODE_POT) J.p = shfl2(J.p, src);
+        }
+        // after 32 rotations lane l holds the sums of particle jb + l
+        if (MODE & NB_MODE_FORCE) {
+            jw[0 * TJ + jb + lane] = sum2(J.x);
+            jw[1 * TJ + jb + lane] = sum2(J.y);
+            jw[2 * TJ + jb + lane] = sum2(J.z);
+        }
+        if (MODE & NB_MODE_POT) jw[3 * TJ + jb + lane] = sum2(J.p);
+    }
+}
+
+// general (per-particle mass / softening) symmetric tile: rare (species boundaries, per-particle softening
+// arrays, padding) -> non-inlined on a copy of the state, like the masked tile of the one-sided sweep
+template <int KID, int MODE, int NP>
+__device__ __noinline__ void sym_tile_f32_general(const unsigned char* stage, SymCold32<NP>* T, const float cmax_i,
+                                                  const float eps2, float* jw, const int lane) {
+    IState<NP> S = T->S;   // work on registers, not on the caller's local-memory copy
+    f2 m[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) m[q] = T->m[q];
+    sym_tile_f32<KID, MODE, false, NP>(stage, S, m, cmax_i, 0.f, eps2, jw, lane);
+    T->S = S;
+}
+
+template <int NP>
+struct SymF32Smem {
+    static constexpr int kStageBytes = STAGES * TILE_BYTES_F32;
+    static constexpr int kBarOff     = (kStageBytes + 63) & ~63;
+    static constexpr int kRunOff     = kBarOff + 64;
+    static constexpr int kRunBytes   = 4 * 2 * NP * THREADS * 4;          // float running sums [4][2NP][THREADS]
+    static constexpr int kJOff       = kRunOff + kRunBytes;
+    static constexpr int kJBytes     = (THREADS / 32) * 4 * TJ * 4;       // j-side slices [warps][4][TJ]
+    static constexpr int kTotal      = kJOff + kJBytes;
+};
+
+template <int KID, int MODE, int NP, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    using L = SymF32Smem<NP>;
+    constexpr int IB  = THREADS * 2 * NP;
+    constexpr int TPB = IB / TJ;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    float* run         = reinterpret_cast<float*>(smem + L::kRunOff);   // [4][2*NP][THREADS]
+    float* jbuf        = reinterpret_cast<float*>(smem + L::kJOff);     // [warps][4][TJ]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x, grid = gridDim.x;
+    const long long u0 = unit_begin(a.total, cta, grid);
+    const long long u1 = unit_begin(a.total, cta + 1, grid);
+    const int n_units  = static_cast<int>(u1 - u0);
+    if (n_units <= 0) return;
+    const float eps2 = static_cast<float>(a.eps2);
+    const long long i_end = static_cast<long long>(a.it0 + a.nT) * TJ;   // first slot past the i-range
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // unit cursor of the consumer (all threads) and of the TMA producer (thread 0 runs STAGES-1 units ahead)
+    int ib        = sym_find_block<TPB>(a, u0);
+    int jl        = static_cast<int>(u0 - sym_prefix<TPB>(a, ib));
+    int cnt       = sym_count<TPB>(a, ib);
+    int t_ib = ib, t_jl = jl, t_cnt = cnt, issued = 0;
+    auto issue_next = [&]() {
+        while (t_jl >= t_cnt) {
+            ++t_ib;
+            t_jl  = 0;
+            t_cnt = sym_count<TPB>(a, t_ib);
+        }
+        bool dg;
+        const int gt  = sym_tile<TPB>(a, t_ib, t_jl, dg);
+        uint64_t* bar = &full_bar[issued % STAGES];
+        mbar_expect_tx(bar, TILE_BYTES_F32);
+        bulk_g2s(smem + (issued % STAGES) * TILE_BYTES_F32, a.packed + static_cast<size_t>(gt) * TILE_BYTES_F32,
+                 TILE_BYTES_F32, bar);
+        ++issued;
+        ++t_jl;
+    };
+    if (tid == 0) {
+        for (int k = 0; k < STAGES - 1 && k < n_units; ++k) issue_next();
+    }
+
+    // j side of the previous symmetric tile: summed over the warps and added to ws after the next barrier
+    bool pend = false;
+    int pend_gt = 0;
+    float pend_scale = 1.f;
+    auto flush_j = [&]() {
+#pragma unroll
+        for (int jj = tid; jj < TJ; jj += THREADS) {
+            double* dst = a.ws + (static_cast<size_t>(pend_gt) * TJ + jj) * 4;
+#pragma unroll
+            for (int comp = 0; comp < 4; ++comp) {
+                if (comp < 3 ? !(MODE & NB_MODE_FORCE) : !(MODE & NB_MODE_POT)) continue;
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < THREADS / 32; ++w) v += static_cast<double>(jbuf[(w * 4 + comp) * TJ + jj]);
+                // a_j += -m_i K dx  (dx = r_j - r_i);  s_phi_j += +m_i / r
+                atomicAdd(dst + comp, (comp < 3 ? -v : v) * static_cast<double>(pend_scale));
+            }
+        }
+    };
+
+    int k = 0;
+    while (k < n_units) {
+        if (jl >= cnt) {
+            ++ib;
+            jl  = 0;
+            cnt = sym_count<TPB>(a, ib);
+            continue;
+        }
+        const int seg = min(cnt - jl, n_units - k);
+
+        // ---- this thread's i-pairs (read straight from the packed records) ----
+        const int tile0          = a.it0 + TPB * ib;
+        const long long ig_block = static_cast<long long>(tile0) * TJ;
+        const long long ig0      = ig_block + 2LL * tid;
+        IState<NP> S;
+        f2 mi[NP];
+        float cmax_i = 0.f;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const long long ig = ig0 + 2LL * THREADS * q;   // even; ig+1 is in the same tile
+            // dummy i beyond the i-range: far away and massless -> contributes nothing, results discarded
+            S.x[q] = S.y[q] = S.z[q] = splat(NB_PAD_POS_F32);
+            S.c0[q] = S.c1[q] = 0.f;
+            mi[q] = 0ull;
+            if (ig < i_end) {
+                const long long t = ig / TJ;
+                const int kk      = static_cast<int>(ig - t * TJ);
+                const float* tb   = reinterpret_cast<const float*>(a.packed + static_cast<size_t>(t) * TILE_BYTES_F32);
+                S.x[q] = *reinterpret_cast<const f2*>(tb + COMP_X * TJ + kk);
+                S.y[q] = *reinterpret_cast<const f2*>(tb + COMP_Y * TJ + kk);
+                S.z[q] = *reinterpret_cast<const f2*>(tb + COMP_Z * TJ + kk);
+                mi[q]  = *reinterpret_cast<const f2*>(tb + COMP_M * TJ + kk);
+                const float2 c2 = *reinterpret_cast<const float2*>(tb + COMP_C * TJ + kk);
+                S.c0[q] = c2.x;
+                S.c1[q] = c2.y;
+            }
+            cmax_i = fmaxf(cmax_i, fmaxf(S.c0[q], S.c1[q]));
+            S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0ull;
+        }
+        // is the whole i-block one species (same mass and softening, no padding, all TPB tiles present)?
+        bool blk_uni = (tile0 + TPB <= a.it0 + a.nT);
+        float cI = 0.f, mI = 0.f;
+        if (blk_uni) {
+#pragma unroll
+            for (int t = 0; t < TPB; ++t) {
+                const float4 meta = *reinterpret_cast<const float4*>(
+                    a.packed + static_cast<size_t>(tile0 + t) * TILE_BYTES_F32 + 5 * TJ * 4);
+                if (t == 0) {
+                    cI = meta.x;
+                    mI = meta.y;
+                }
+                blk_uni = blk_uni && (meta.x == cI) && (meta.y == mI);   // NaN (non-uniform tile) fails both
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4 * 2 * NP; ++e) run[e * THREADS + tid] = 0.f;
+        int tiles_in_run = 0;
+
+        auto flush_i = [&]() {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const long long ig = ig0 + 2LL * THREADS * q + half;
+                    double* dst = a.ws + static_cast<size_t>(ig) * 4;
+#pragma unroll
+                    for (int comp = 0; comp < 4; ++comp) {
+                        if (comp < 3 ? !(MODE & NB_MODE_FORCE) : !(MODE & NB_MODE_POT)) continue;
+                        float* r = &run[((comp * 2 * NP) + 2 * q + half) * THREADS + tid];
+                        if (ig < i_end) atomicAdd(dst + comp, static_cast<double>(*r));
+                        *r = 0.f;
+                    }
+                }
+            }
+        };
+
+        for (int t = 0; t < seg; ++t, ++k, ++jl) {
+            __syncthreads();   // everyone is done with tile k-1: its stage may be refilled, its j-slices are complete
+            if (tid == 0 && issued < n_units) issue_next();
+            if (pend) {
+                flush_j();
+                __syncthreads();   // slices are free again
+                pend = false;
+            }
+            mbar_wait(&full_bar[k % STAGES], (k / STAGES) & 1);
+
+            bool diag;
+            const int gt = sym_tile<TPB>(a, ib, jl, diag);
+            const unsigned char* stage = smem + (k % STAGES) * TILE_BYTES_F32;
+            const float4 meta = *reinterpret_cast<const float4*>(stage + 5 * TJ * 4);   // {c_uni|NaN, m_uni|NaN, c_max, -}
+            float m_fold = 1.f;
+            if (diag) {
+                IState<NP> T = S;
+                tile_f32_masked<KID, MODE, NP, 4>(stage, &T, eps2, static_cast<long long>(gt) * TJ, ig0, a.n_j);
+                S = T;
+            } else {
+                float* jw = jbuf + warp * 4 * TJ;
+                if (blk_uni && meta.x == meta.x && meta.y == meta.y) {
+                    m_fold     = meta.y;
+                    pend_scale = mI;
+                    sym_tile_f32<KID, MODE, true, NP>(stage, S, mi, cmax_i, fmaxf(cI, meta.x), eps2, jw, lane);
+                } else {
+                    pend_scale = 1.f;
+                    SymCold32<NP> T;
+                    T.S = S;
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) T.m[q] = mi[q];
+                    sym_tile_f32_general<KID, MODE, NP>(stage, &T, cmax_i, eps2, jw, lane);
+                    S = T.S;
+                }
+                pend    = true;
+                pend_gt = gt;
+            }
+
+            // fold this tile's partial sums (x tile mass) into the float running sums
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                auto fold = [&](int comp, f2 v) {
+                    float lo, hi;
+                    upk(v, lo, hi);
+                    float* r0 = &run[((comp * 2 * NP) + 2 * q) * THREADS + tid];
+                    float* r1 = &run[((comp * 2 * NP) + 2 * q + 1) * THREADS + tid];
+                    *r0 = fmaf(lo, m_fold, *r0);
+                    *r1 = fmaf(hi, m_fold, *r1);
+                };
+                if (MODE & NB_MODE_FORCE) {
+                    fold(0, S.ax[q]);
+                    fold(1, S.ay[q]);
+                    fold(2, S.az[q]);
+                }
+                if (MODE & NB_MODE_POT) fold(3, S.sp[q]);
+                S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0ull;
+            }
+            if (++tiles_in_run == SYM_FLUSH_TILES) {
+                flush_i();
+                tiles_in_run = 0;
+            }
+        }
+        if (tiles_in_run) flush_i();
+    }
+    __syncthreads();
+    if (pend) flush_j();
+}
+
+}  // namespace nb

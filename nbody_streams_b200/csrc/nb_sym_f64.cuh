@@ -1,0 +1,427 @@
+// nb_sym_f64.cuh — pair-symmetric FP64 sweep (NB_PREC_F64), the large-N path.
+//
+// Same job as nb_sweep_f64.cuh (replaces nbody_forces_kernel<double> / nbody_potential_kernel<double>,
+// reference cuda_kernels.py:755-864, :1299-1387) with every unordered pair evaluated once (nb_sym.cuh) and
+// the same systolic structure as nb_sym_f32.cuh: NI = 4 i-particles per thread in registers, one j-particle
+// per lane per step, travelling j-accumulators rotated with SHFL, per-warp j-slices in shared memory added
+// to the double workspace after every tile.  Per pair: 3 DADD + 3 DFMA + rsqrt (MUFU.RSQ64H + 5) + 2 DMUL +
+// 6 DFMA = 19 FP64 instructions for TWO interactions (the one-sided sweep: 16 per interaction).
+// The i-side sums stay in double for the whole segment (registers per tile, shared-memory running sums
+// across tiles because uniform tiles are accumulated unweighted and scaled by the tile mass per tile).
+#pragma once
+#include "nb_sweep_f64.cuh"
+#include "nb_sym.cuh"
+
+namespace nb {
+
+constexpr int SYM_NI_F64     = 4;                       // i-particles per thread
+constexpr int SYM_IB_F64     = THREADS * SYM_NI_F64;    // 512 per CTA
+constexpr int SYM_TPB_F64    = SYM_IB_F64 / TJ;         // 2 tiles per i-block
+constexpr int SYM_STAGES_F64 = 2;                       // a tile takes ~40k cycles to sweep: one tile of prefetch is plenty
+
+__device__ __forceinline__ double shfl_d(const double v, const int src) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
+
+struct JAcc64 {
+    double x, y, z, p;
+};
+
+// mass-less kernel factors of one pair from d = r^2 + softening term: w (1/r^3-like), p (1/r-like)
+template <int KID, int MODE>
+__device__ __forceinline__ void sym_factors_f64(const double d, const double h2, const double eps2, double& w,
+                                                double& p) {
+    const double rinv  = rsqrt_f64(d);
+    const double rinv2 = rinv * rinv;
+    p = rinv;
+    w = 0.0;
+    if (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2) {
+        const double t = (h2 - eps2) * rinv2;   // c = h^2 + eps2 seeds the r^2 chain; the terms use bare h^2
+        if (MODE & NB_MODE_POT)
+            p = rinv * ((KID == NB_KERNEL_DEHNEN_K1) ? fma(0.5, t, 1.0) : fma(t, fma(0.375, t, 0.5), 1.0));
+        if (MODE & NB_MODE_FORCE)
+            w = (rinv * rinv2) * ((KID == NB_KERNEL_DEHNEN_K1) ? fma(1.5, t, 1.0) : fma(t, fma(3.75, t, 1.5), 1.0));
+    } else if (MODE & NB_MODE_FORCE) {
+        w = rinv * rinv2;
+    }
+}
+
+template <int MODE, bool U>
+__device__ __forceinline__ void sym_apply_f64(const double w, const double p, const double dx, const double dy,
+                                              const double dz, const double mj, const double mi, double& ax,
+                                              double& ay, double& az, double& sp, JAcc64& J) {
+    if (U) {
+        if (MODE & NB_MODE_POT) {
+            sp += p;
+            J.p += p;
+        }
+        if (MODE & NB_MODE_FORCE) {
+            ax  = fma(w, dx, ax);
+            ay  = fma(w, dy, ay);
+            az  = fma(w, dz, az);
+            J.x = fma(w, dx, J.x);
+            J.y = fma(w, dy, J.y);
+            J.z = fma(w, dz, J.z);
+        }
+    } else {
+        if (MODE & NB_MODE_POT) {
+            sp  = fma(mj, p, sp);
+            J.p = fma(mi, p, J.p);
+        }
+        if (MODE & NB_MODE_FORCE) {
+            const double fi = mj * w, fj = mi * w;
+            ax  = fma(fi, dx, ax);
+            ay  = fma(fi, dy, ay);
+            az  = fma(fi, dz, az);
+            J.x = fma(fj, dx, J.x);
+            J.y = fma(fj, dy, J.y);
+            J.z = fma(fj, dz, J.z);
+        }
+    }
+}
+
+template <int NI>
+struct SymCold64 {
+    IState64<NI> S;
+    double m[NI];
+    JAcc64 J;
+};
+
+// the whole step (NI i x this lane's j) with the exact cubic spline (reference cuda_kernels.py:687-752,
+// :1228-1297 restated in spline_inside); U: unweighted sums
+template <int MODE, bool U, int NI>
+__device__ __noinline__ void sym_spline_exact_step_f64(SymCold64<NI>* T, const double xj, const double yj,
+                                                       const double zj, const double mj_in, const double cj,
+                                                       const double eps2) {
+    const double mj = U ? 1.0 : mj_in;
+#pragma unroll
+    for (int q = 0; q < NI; ++q) {
+        const double dx = xj - T->S.x[q], dy = yj - T->S.y[q], dz = zj - T->S.z[q];
+        const double d  = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+        const double h2 = fmax(cj, T->S.c[q]);
+        const double ri = rsqrt_f64(d);
+        double w, p;
+        if (d < h2) {
+            spline_inside<double>(d, ri, rsqrt_f64(h2), w, p);
+        } else {
+            p = ri;
+            w = ri * (ri * ri);
+        }
+        sym_apply_f64<MODE, false>(w, p, dx, dy, dz, mj, U ? 1.0 : T->m[q], T->S.ax[q], T->S.ay[q], T->S.az[q],
+                                   T->S.sp[q], T->J);
+    }
+}
+
+// one symmetric j-tile; jw = this warp's slice [4][TJ] of the j-side buffer
+template <int KID, int MODE, bool U, int NI>
+__device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ stage, IState64<NI>& S,
+                                             const double (&mi)[NI], const double cmax_i, const double c_pair,
+                                             const double eps2, double* __restrict__ jw, const int lane) {
+    const double* __restrict__ sX = reinterpret_cast<const double*>(stage) + COMP_X * TJ;
+    const double* __restrict__ sY = reinterpret_cast<const double*>(stage) + COMP_Y * TJ;
+    const double* __restrict__ sZ = reinterpret_cast<const double*>(stage) + COMP_Z * TJ;
+    const double* __restrict__ sM = reinterpret_cast<const double*>(stage) + COMP_M * TJ;
+    const double* __restrict__ sC = reinterpret_cast<const double*>(stage) + COMP_C * TJ;
+    constexpr bool kUsesC = (KID == NB_KERNEL_PLUMMER || KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
+    const int src = (lane + 1) & 31;
+
+#pragma unroll 1
+    for (int rho = 0; rho < TJ / 32; ++rho) {
+        JAcc64 J;
+        J.x = J.y = J.z = J.p = 0.0;
+        const int jb = 32 * rho;
+#pragma unroll 1
+        for (int s = 0; s < 32; ++s) {
+            const int jj    = jb + ((lane + s) & 31);
+            const double xj = sX[jj], yj = sY[jj], zj = sZ[jj];
+            double mj = 1.0, cj = c_pair;
+            if (!U) {
+                mj = sM[jj];
+                cj = sC[jj];
+            }
+            if (KID != NB_KERNEL_SPLINE) {
+#pragma unroll
+                for (int q = 0; q < NI; ++q) {
+                    const double dx = xj - S.x[q], dy = yj - S.y[q], dz = zj - S.z[q];
+                    double h2, c;
+                    if (KID == NB_KERNEL_NEWTONIAN) {
+                        h2 = c = eps2;
+                    } else {
+                        h2 = U ? c_pair : fmax(cj, S.c[q]);
+                        c  = kUsesC ? h2 : eps2;
+                    }
+                    const double d = fma(dx, dx, fma(dy, dy, fma(dz, dz, c)));
+                    double w, p;
+                    sym_factors_f64<KID, MODE>(d, h2, eps2, w, p);
+                    sym_apply_f64<MODE, U>(w, p, dx, dy, dz, mj, mi[q], S.ax[q], S.ay[q], S.az[q], S.sp[q], J);
+                }
+            } else {
+                // two-phase: r^2 of the step first, minimum tracked through the high words (monotonic for
+                // positive doubles); Newtonian finish unless some pair may lie inside its softening length
+                double dx[NI], dy[NI], dz[NI], d[NI];
+                int hi_min = 0x7fffffff;
+#pragma unroll
+                for (int q = 0; q < NI; ++q) {
+                    dx[q]  = xj - S.x[q];
+                    dy[q]  = yj - S.y[q];
+                    dz[q]  = zj - S.z[q];
+                    d[q]   = fma(dx[q], dx[q], fma(dy[q], dy[q], fma(dz[q], dz[q], eps2)));
+                    hi_min = min(hi_min, __double2hiint(d[q]));
+                }
+                const double h2lim = U ? c_pair : fmax(cj, cmax_i);
+                if (hi_min <= __double2hiint(h2lim)) {
+                    SymCold64<NI> T;
+                    T.S = S;
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) T.m[q] = mi[q];
+                    T.J = J;
+                    sym_spline_exact_step_f64<MODE, U, NI>(&T, xj, yj, zj, mj, cj, eps2);
+                    S = T.S;
+                    J = T.J;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        const double rinv = rsqrt_f64(d[q]);
+                        const double w    = (MODE & NB_MODE_FORCE) ? rinv * (rinv * rinv) : 0.0;
+                        sym_apply_f64<MODE, U>(w, rinv, dx[q], dy[q], dz[q], mj, mi[q], S.ax[q], S.ay[q], S.az[q],
+                                               S.sp[q], J);
+                    }
+                }
+            }
+            // systolic rotation: the accumulators follow their j-particle to the lane that meets it next
+            if (MODE & NB_MODE_FORCE) {
+                J.x = shfl_d(J.x, src);
+                J.y = shfl_d(J.y, src);
+                J.z = shfl_d(J.z, src);
+            }
+            if (MODE & NB_MODE_POT) J.p = shfl_d(J.p, src);
+        }
+        if (MODE & NB_MODE_FORCE) {
+            jw[0 * TJ + jb + lane] = J.x;
+            jw[1 * TJ + jb + lane] = J.y;
+            jw[2 * TJ + jb + lane] = J.z;
+        }
+        if (MODE & NB_MODE_POT) jw[3 * TJ + jb + lane] = J.p;
+    }
+}
+
+template <int KID, int MODE, int NI>
+__device__ __noinline__ void sym_tile_f64_general(const unsigned char* stage, SymCold64<NI>* T, const double cmax_i,
+                                                  const double eps2, double* jw, const int lane) {
+    IState64<NI> S = T->S;   // work on registers, not on the caller's local-memory copy
+    double m[NI];
+#pragma unroll
+    for (int q = 0; q < NI; ++q) m[q] = T->m[q];
+    sym_tile_f64<KID, MODE, false, NI>(stage, S, m, cmax_i, 0.0, eps2, jw, lane);
+    T->S = S;
+}
+
+// diagonal tile (overlaps the CTA's own i-block): one-sided masked path of nb_sweep_f64.cuh on a state copy
+template <int KID, int MODE, int NI>
+__device__ __noinline__ void sym_tile_f64_diag(const unsigned char* stage, IState64<NI>* T, const double eps2,
+                                               const long long jg0, const long long ig0, const long long n_j) {
+    tile_f64<KID, MODE, true, false, false, NI>(stage, *T, eps2, 0.0, jg0, ig0, n_j);
+}
+
+template <int NI>
+struct SymF64Smem {
+    static constexpr int kStageBytes = SYM_STAGES_F64 * TILE_BYTES_F64;
+    static constexpr int kBarOff     = (kStageBytes + 63) & ~63;
+    static constexpr int kRunOff     = kBarOff + 64;
+    static constexpr int kRunBytes   = 4 * NI * THREADS * 8;              // double running sums [4][NI][THREADS]
+    static constexpr int kJOff       = kRunOff + kRunBytes;
+    static constexpr int kJBytes     = (THREADS / 32) * 4 * TJ * 8;       // j-side slices [warps][4][TJ]
+    static constexpr int kTotal      = kJOff + kJBytes;
+};
+
+template <int KID, int MODE, int NI, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    using L = SymF64Smem<NI>;
+    constexpr int NSTG = SYM_STAGES_F64;
+    constexpr int IB   = THREADS * NI;
+    constexpr int TPB  = IB / TJ;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    double* run        = reinterpret_cast<double*>(smem + L::kRunOff);   // [4][NI][THREADS]
+    double* jbuf       = reinterpret_cast<double*>(smem + L::kJOff);     // [warps][4][TJ]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x, grid = gridDim.x;
+    const long long u0 = unit_begin(a.total, cta, grid);
+    const long long u1 = unit_begin(a.total, cta + 1, grid);
+    const int n_units  = static_cast<int>(u1 - u0);
+    if (n_units <= 0) return;
+    const double eps2     = a.eps2;
+    const long long i_end = static_cast<long long>(a.it0 + a.nT) * TJ;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTG; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    int ib  = sym_find_block<TPB>(a, u0);
+    int jl  = static_cast<int>(u0 - sym_prefix<TPB>(a, ib));
+    int cnt = sym_count<TPB>(a, ib);
+    int t_ib = ib, t_jl = jl, t_cnt = cnt, issued = 0;
+    auto issue_next = [&]() {
+        while (t_jl >= t_cnt) {
+            ++t_ib;
+            t_jl  = 0;
+            t_cnt = sym_count<TPB>(a, t_ib);
+        }
+        bool dg;
+        const int gt  = sym_tile<TPB>(a, t_ib, t_jl, dg);
+        uint64_t* bar = &full_bar[issued % NSTG];
+        mbar_expect_tx(bar, TILE_BYTES_F64);
+        bulk_g2s(smem + (issued % NSTG) * TILE_BYTES_F64, a.packed + static_cast<size_t>(gt) * TILE_BYTES_F64,
+                 TILE_BYTES_F64, bar);
+        ++issued;
+        ++t_jl;
+    };
+    if (tid == 0) {
+        for (int k = 0; k < NSTG - 1 && k < n_units; ++k) issue_next();
+    }
+
+    bool pend = false;
+    int pend_gt = 0;
+    double pend_scale = 1.0;
+    auto flush_j = [&]() {
+#pragma unroll
+        for (int jj = tid; jj < TJ; jj += THREADS) {
+            double* dst = a.ws + (static_cast<size_t>(pend_gt) * TJ + jj) * 4;
+#pragma unroll
+            for (int comp = 0; comp < 4; ++comp) {
+                if (comp < 3 ? !(MODE & NB_MODE_FORCE) : !(MODE & NB_MODE_POT)) continue;
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < THREADS / 32; ++w) v += jbuf[(w * 4 + comp) * TJ + jj];
+                atomicAdd(dst + comp, (comp < 3 ? -v : v) * pend_scale);   // a_j += -m_i K dx ; s_phi_j += m_i / r
+            }
+        }
+    };
+
+    int k = 0;
+    while (k < n_units) {
+        if (jl >= cnt) {
+            ++ib;
+            jl  = 0;
+            cnt = sym_count<TPB>(a, ib);
+            continue;
+        }
+        const int seg = min(cnt - jl, n_units - k);
+
+        const int tile0          = a.it0 + TPB * ib;
+        const long long ig_block = static_cast<long long>(tile0) * TJ;
+        const long long ig0      = ig_block + tid;
+        IState64<NI> S;
+        double mi[NI];
+        double cmax_i = 0.0;
+#pragma unroll
+        for (int q = 0; q < NI; ++q) {
+            const long long ig = ig0 + static_cast<long long>(THREADS) * q;
+            S.x[q] = S.y[q] = S.z[q] = NB_PAD_POS_F64;   // dummy i beyond the i-range: far away, massless
+            S.c[q] = 0.0;
+            mi[q]  = 0.0;
+            if (ig < i_end) {
+                const long long t = ig / TJ;
+                const int kk      = static_cast<int>(ig - t * TJ);
+                const double* tb  = reinterpret_cast<const double*>(a.packed + static_cast<size_t>(t) * TILE_BYTES_F64);
+                S.x[q] = tb[COMP_X * TJ + kk];
+                S.y[q] = tb[COMP_Y * TJ + kk];
+                S.z[q] = tb[COMP_Z * TJ + kk];
+                mi[q]  = tb[COMP_M * TJ + kk];
+                S.c[q] = tb[COMP_C * TJ + kk];
+            }
+            cmax_i = fmax(cmax_i, S.c[q]);
+            S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0.0;
+        }
+        bool blk_uni = (tile0 + TPB <= a.it0 + a.nT);
+        double cI = 0.0, mI = 0.0;
+        if (blk_uni) {
+#pragma unroll
+            for (int t = 0; t < TPB; ++t) {
+                const double2 meta = *reinterpret_cast<const double2*>(
+                    a.packed + static_cast<size_t>(tile0 + t) * TILE_BYTES_F64 + 5 * TJ * 8);
+                if (t == 0) {
+                    cI = meta.x;
+                    mI = meta.y;
+                }
+                blk_uni = blk_uni && (meta.x == cI) && (meta.y == mI);   // NaN (non-uniform tile) fails both
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4 * NI; ++e) run[e * THREADS + tid] = 0.0;
+
+        for (int t = 0; t < seg; ++t, ++k, ++jl) {
+            __syncthreads();   // everyone is done with tile k-1: its stage may be refilled, its j-slices are complete
+            if (tid == 0 && issued < n_units) issue_next();
+            if (pend) {
+                flush_j();
+                __syncthreads();
+                pend = false;
+            }
+            mbar_wait(&full_bar[k % NSTG], (k / NSTG) & 1);
+
+            bool diag;
+            const int gt = sym_tile<TPB>(a, ib, jl, diag);
+            const unsigned char* stage = smem + (k % NSTG) * TILE_BYTES_F64;
+            const double2 meta = *reinterpret_cast<const double2*>(stage + 5 * TJ * 8);   // {c_uni, m_uni} or NaN
+            double m_fold = 1.0;
+            if (diag) {
+                IState64<NI> T = S;
+                sym_tile_f64_diag<KID, MODE, NI>(stage, &T, eps2, static_cast<long long>(gt) * TJ, ig0, a.n_j);
+                S = T;
+            } else {
+                double* jw = jbuf + warp * 4 * TJ;
+                if (blk_uni && meta.x == meta.x && meta.y == meta.y) {
+                    m_fold     = meta.y;
+                    pend_scale = mI;
+                    sym_tile_f64<KID, MODE, true, NI>(stage, S, mi, cmax_i, fmax(cI, meta.x), eps2, jw, lane);
+                } else {
+                    pend_scale = 1.0;
+                    SymCold64<NI> T;
+                    T.S = S;
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) T.m[q] = mi[q];
+                    sym_tile_f64_general<KID, MODE, NI>(stage, &T, cmax_i, eps2, jw, lane);
+                    S = T.S;
+                }
+                pend    = true;
+                pend_gt = gt;
+            }
+#pragma unroll
+            for (int q = 0; q < NI; ++q) {
+                if (MODE & NB_MODE_FORCE) {
+                    run[(0 * NI + q) * THREADS + tid] = fma(S.ax[q], m_fold, run[(0 * NI + q) * THREADS + tid]);
+                    run[(1 * NI + q) * THREADS + tid] = fma(S.ay[q], m_fold, run[(1 * NI + q) * THREADS + tid]);
+                    run[(2 * NI + q) * THREADS + tid] = fma(S.az[q], m_fold, run[(2 * NI + q) * THREADS + tid]);
+                }
+                if (MODE & NB_MODE_POT)
+                    run[(3 * NI + q) * THREADS + tid] = fma(S.sp[q], m_fold, run[(3 * NI + q) * THREADS + tid]);
+                S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0.0;
+            }
+        }
+        // segment done: add this block's i-side sums to the workspace
+#pragma unroll
+        for (int q = 0; q < NI; ++q) {
+            const long long ig = ig0 + static_cast<long long>(THREADS) * q;
+            if (ig < i_end) {
+                double* dst = a.ws + static_cast<size_t>(ig) * 4;
+#pragma unroll
+                for (int comp = 0; comp < 4; ++comp) {
+                    if (comp < 3 ? !(MODE & NB_MODE_FORCE) : !(MODE & NB_MODE_POT)) continue;
+                    atomicAdd(dst + comp, run[(comp * NI + q) * THREADS + tid]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (pend) flush_j();
+}
+
+}  // namespace nb

@@ -1,0 +1,3 @@
+// pair-symmetric sweeps, softening kernel id 4 (see nb_sym_dispatch.cuh)
+#include "nb_sym_dispatch.cuh"
+NB_SYM_DEFINE_KID(4)

@@ -183,15 +183,27 @@ _GRID_CACHE: dict = {}
 _SCRATCH: dict = {}
 
 
-def _grid_for(prec: int, kernel_id: int, mode: int, device) -> int:
+def _grid_for(prec: int, kernel_id: int, mode: int, device, sym: bool = False) -> int:
     lib = _lib.load()
-    key = (device.index, prec, kernel_id, mode, lib.nb_get_variant(prec))
+    key = (device.index, prec, kernel_id, mode, "sym" if sym else lib.nb_get_variant(prec))
     g = _GRID_CACHE.get(key)
     if g is None:
         out = C.c_int(0)
-        _lib.check(lib.nb_sweep_grid(prec, kernel_id, mode, C.byref(out)))
+        query = lib.nb_sym_grid if sym else lib.nb_sweep_grid
+        _lib.check(query(prec, kernel_id, mode, C.byref(out)))
         g = _GRID_CACHE[key] = int(out.value)
     return g
+
+
+def use_symmetric(N: int, algorithm: str | None = None) -> bool:
+    """Which sweep evaluates an all-pairs problem of N particles: the pair-symmetric one (every unordered
+    pair once, applied to both particles; large N) or the one-sided one (every ordered pair, bitwise
+    reproducible, finer work units; small N).  `algorithm`: None/'auto', 'symmetric' or 'onesided'."""
+    if algorithm in (None, "auto"):
+        return N >= _lib.load().nb_sym_min_n()
+    if algorithm not in ("symmetric", "onesided"):
+        raise ValueError(f"algorithm must be 'auto', 'symmetric' or 'onesided', got {algorithm!r}")
+    return algorithm == "symmetric"
 
 
 def _scratch(device, tag: str, nbytes: int):
@@ -233,7 +245,7 @@ def _device_operand(arr_cpu, scalar, original, dtype_t, device):
 
 
 def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, mode, G, eps2, dtype_np, group=None,
-                n_sources=None):
+                n_sources=None, algorithm=None):
     """pack + sweep + finish on the current stream.  Returns (acc|None, phi|None) torch tensors.
 
     With a torch.distributed `group` of more than one rank every rank packs all N particles, sweeps only
@@ -264,7 +276,14 @@ def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, m
         h_ptr, h_dt = (h_t.data_ptr(), _dt_code(h_t)) if h_t is not None else (None, 0)
         acc_ptr = acc.data_ptr() if acc is not None else None
         phi_ptr = phi.data_ptr() if phi is not None else None
-        if world == 1 and n_sources is None:
+        if world == 1 and n_sources is None and use_symmetric(N, algorithm):
+            grid = _grid_for(prec, kernel_id, mode, device, sym=True)
+            ws_bytes = lib.nb_sym_workspace_bytes(lib.nb_padded_count(N))
+            ws = _scratch(device, "workspace", ws_bytes)
+            _lib.check(lib.nb_direct_sym(prec, kernel_id, mode, pos_t.data_ptr(), _dt_code(pos_t), mass_ptr, mass_dt,
+                                         float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, float(G), float(eps2),
+                                         packed.data_ptr(), ws.data_ptr(), ws_bytes, grid, acc_ptr, phi_ptr, stream))
+        elif world == 1 and n_sources is None:
             ws_bytes = lib.nb_workspace_bytes(prec, N, grid, 1)
             ws = _scratch(device, "workspace", ws_bytes)
             _lib.check(lib.nb_direct(prec, kernel_id, mode, pos_t.data_ptr(), _dt_code(pos_t), mass_ptr, mass_dt,
@@ -362,6 +381,7 @@ def compute_nbody_forces_gpu(
     device=None,
     group=None,
     n_sources=None,
+    algorithm=None,
 ):
     """Direct-summation gravitational accelerations on the GPU.
 
@@ -381,7 +401,8 @@ def compute_nbody_forces_gpu(
     GPU) shards the i-particles over its ranks and all-gathers the result,
     ``n_sources`` makes only the first n_sources particles gravitating sources
     (the others are massless test particles and their source tiles are never
-    swept: N x n_sources pair work, used by ``unbind.iterative_unbinding``).
+    swept: N x n_sources pair work, used by ``unbind.iterative_unbinding``),
+    ``algorithm`` ('auto' | 'symmetric' | 'onesided', see :func:`use_symmetric`).
 
     Raises ImportError without a CUDA device / built library, ValueError for
     bad shapes, precision or kernel names, RuntimeError for CUDA failures.
@@ -391,7 +412,7 @@ def compute_nbody_forces_gpu(
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
     mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
-    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np, group, n_src)
+    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np, group, n_src, algorithm)
     if return_cupy:
         return acc.as_subclass(DeviceArray)
     return acc.cpu().numpy()
@@ -411,6 +432,7 @@ def compute_nbody_potential_gpu(
     device=None,
     group=None,
     n_sources=None,
+    algorithm=None,
 ):
     """Gravitational potential at each particle, ``phi_i = G sum_{j != i} m_j Phi(r_ij)``.
 
@@ -424,7 +446,7 @@ def compute_nbody_potential_gpu(
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
     mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
-    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np, group, n_src)
+    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np, group, n_src, algorithm)
     if return_cupy:
         return phi.as_subclass(DeviceArray)
     return phi.cpu().numpy()
@@ -444,6 +466,7 @@ def compute_nbody_forces_potential_gpu(
     device=None,
     group=None,
     n_sources=None,
+    algorithm=None,
 ):
     """Accelerations AND potential from one fused sweep (new; the reference needs two
     O(N^2) passes, run.py:611-634).  Returns ``(acc (N,3), phi (N,))``."""
@@ -452,7 +475,7 @@ def compute_nbody_forces_potential_gpu(
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
     mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
-    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np, group, n_src)
+    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np, group, n_src, algorithm)
     if return_cupy:
         return acc.as_subclass(DeviceArray), phi.as_subclass(DeviceArray)
     return acc.cpu().numpy(), phi.cpu().numpy()
