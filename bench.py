@@ -9,9 +9,12 @@ direct-summation path at N = 1M (BASELINE.json), 1/2/4/8 GPUs.
 Workload (config 3 of BASELINE.json): make_plummer_sphere(1_000_000, M_total=1e9, a=1.0, seed=42069),
 scalar softening 0.01, precision 'float32_kahan', kernel 'plummer', force AND potential.
 One "step" = one KDK leapfrog step of the whole system = one fused kick+drift+repack, the all-gather of
-the j-records (N > 1), ONE force+potential sweep over all N^2 pairs, the fix-up and the closing half kick.
-Interactions per step = N^2 (reference convention, fields.py:1317).  Total work is fixed as GPUs are
-added ("scaling": "strong").
+the j-records (N > 1), ONE force+potential sweep over all pairs, the finish kernel (reduce-scatter of the
+partial sums first when N > 1) and the closing half kick.
+Interactions per step = N^2 (reference convention, fields.py:1317: every ordered pair counts).  The default
+sweep is the pair-symmetric one: it evaluates each unordered pair once and applies the result to both
+particles, i.e. N^2/2 kernel evaluations deliver the N^2 interactions (--algorithm onesided times the
+round-1 sweep that evaluates all N^2).  Total work is fixed as GPUs are added ("scaling": "strong").
 
 The JSON line carries, besides the driver contract keys:
   roofline      FP32 CUDA-core roofline of the dominant kernel (the pair sweep): 20 flop/interaction
@@ -20,7 +23,11 @@ The JSON line carries, besides the driver contract keys:
   cpu_baseline  the oracle port of the reference's Numba path timed on this box's host cores on a bounded
                 row sample of the same workload (N = 1 only);
   e2e           the same metric through the public host-array API (compute_nbody_forces_potential_gpu with
-                NumPy in / NumPy out): H2D of positions and D2H of acc+phi inside the timed region.
+                NumPy in / NumPy out): H2D of positions and D2H of acc+phi inside the timed region;
+  parity        outside the timed region: acc and phi of rank 0's first rows after the last step against the
+                float64 oracle on the same (float32-rounded) positions — relative RMS, at every GPU count;
+  ref_gpu_kernel  (1 GPU) the reference's own CUDA kernel, compiled for sm_100 with its flags into baseline/_ref
+                by tools/make_ref_gpu_baseline.py, timed on the same GPU next to this package's sweep.
 """
 from __future__ import annotations
 
@@ -42,6 +49,7 @@ sys.path.insert(0, str(ROOT))
 FLOPS_PER_INTERACTION = 20.0          # BASELINE.json convention
 print_json = None
 FP32_PEAK_NOMINAL_TF = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x lanes x 2 x max SM clock
+TRAFFIC_SYM_N1M = None   # dram bytes per launch of nb::sym_f32_kernel at N=1M from ncu (profiles/r02_*); set once captured
 
 
 def parse():
@@ -55,7 +63,11 @@ def parse():
     p.add_argument("--precision", default="float32_kahan")
     p.add_argument("--softening", type=float, default=0.01)
     p.add_argument("--dt", type=float, default=1e-4)
-    p.add_argument("--no-overlap", action="store_true", help="global summation order (deterministic) at N>1")
+    p.add_argument("--no-overlap", action="store_true", help="no local-shard sweep while the exchange is in flight (N>1)")
+    p.add_argument("--algorithm", default="auto", choices=["auto", "symmetric", "onesided"],
+                   help="pair-symmetric sweep (default from nb_sym_min_n() particles on) or the one-sided sweep")
+    p.add_argument("--parity-rows", type=int, default=2048, help="rows of rank 0 checked against the oracle (0 = skip)")
+    p.add_argument("--skip-ref-gpu", action="store_true")
     p.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
                    help="N>1: NCCL all-gather of the j-records, or the exchange fused into the drift kernel (NVLink stores)")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
@@ -104,6 +116,12 @@ class ClockSampler:
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def config_dict(args, N) -> dict:
+    """Identical for both arms (the driver compares the dicts)."""
+    return {"workload": f"Plummer N={N} direct {args.precision} force+potential, kernel={args.kernel}, "
+                        f"softening={args.softening} (BASELINE config 3)"}
 
 
 def workload(args):
@@ -164,10 +182,9 @@ def run_reference(args):
         "impl": "reference", "metric": "pairwise interactions/s", "value": val, "unit": "interactions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": N * N / val * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Plummer N={N} direct {args.precision} force+potential, kernel={args.kernel}, "
-                               f"softening={args.softening} (BASELINE config 3)",
-                   "note": "reference CPU algorithm (C/OpenMP port of the Numba path; the reference is Python and "
-                           "cannot travel to the GPU box); ms_per_step extrapolates the sampled rate to N^2"},
+        "config": config_dict(args, N),
+        "details": {"note": "reference CPU algorithm (C/OpenMP port of the Numba path; the reference is Python and "
+                            "cannot travel to the GPU box); ms_per_step extrapolates the sampled rate to N^2"},
         "cpu_baseline": {**{k: res[-1][k] for k in ("unit", "cores", "kind", "sample")}, "value": val},
         "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -222,7 +239,7 @@ def main():
     peak_tf = 2.0 * ops.value / 1e12
 
     eng = DirectEngine(N, float(m[0]), args.softening, prec, kid, nb.G_DEFAULT, EPS2_DEFAULT[args.precision], device,
-                       overlap=not args.no_overlap, exchange=args.exchange)
+                       overlap=not args.no_overlap, exchange=args.exchange, algorithm=args.algorithm)
     eng.load_state(xv)
     eng.compute(MODE_BOTH, positions_changed=False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
@@ -256,7 +273,7 @@ def main():
     elapsed_ms = e0.elapsed_time(e1)
     gpu_launches = eng.launches - launches0 + args.steps       # + the L2-flush memset per step (torch kernel)
     sweep_ms = [a.elapsed_time(b) for a, b, _ in eng.sweep_events]
-    sweep_tiles = [t for _, _, t in eng.sweep_events]
+    sweep_tags = [t for _, _, t in eng.sweep_events]
     eng.sweep_events = None
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -264,27 +281,89 @@ def main():
     elapsed_ms = float(t.item())
     value = args.steps * float(N) * float(N) / (elapsed_ms * 1e-3)
 
-    # roofline of the dominant kernel (the pair sweep) on this rank: flops per launch / launch duration
-    inter_per_launch = [eng.n_local * tiles * 256.0 for tiles in sweep_tiles]
+    # ---- roofline of the dominant kernel (the pair sweep) on this rank: algorithmic flops per launch / duration.
+    # Interactions credited to a launch = ordered pairs it delivers (reference convention): a one-sided launch
+    # over T j-tiles delivers n_local x 256 T; a symmetric launch delivers (own shard)^2 for the triangle plus
+    # 2 x (own shard) x (particles of the rectangle ranges).
+    def real(t0, t1):
+        return float(max(0, min(N, t1 * 256) - min(N, t0 * 256)))
+
+    if eng.symmetric:
+        from nbody_streams_b200.engine import sym_plan
+
+        plan = sym_plan(eng.layout, eng.rank, lib.nb_sym_block_tiles(prec))
+        own = real(*plan["own"])
+        nb_ib = max(1, plan["n_ib"])
+        rect = 2.0 * own * (real(*plan["A"]) + real(*plan["B"])) \
+            + 2.0 * own * real(*plan["C"]) * (plan["ibC"][1] - plan["ibC"][0]) / nb_ib
+        credit = {"tri": own * own, "rect": rect, "all": own * own + rect}
+        inter_per_launch = [credit[tag] for tag in sweep_tags]
+        kernel_name = "nb::sym_f32_kernel" if args.precision != "float64" else "nb::sym_f64_kernel"
+    else:
+        inter_per_launch = [eng.n_local * tiles * 256.0 for tiles in sweep_tags]
+        kernel_name = "nb::sweep_f32_kernel" if args.precision != "float64" else "nb::sweep_f64_kernel"
     sweep_total_ms = float(np.sum(sweep_ms))
     achieved_tf = FLOPS_PER_INTERACTION * float(np.sum(inter_per_launch)) / (sweep_total_ms * 1e-3) / 1e12
+    # per-slot launch times, max over ranks (slot = position of the launch inside a step)
+    per_step = max(1, len(sweep_ms) // max(1, args.steps))
+    slot_ms = [float(np.mean(sweep_ms[k::per_step])) for k in range(per_step)]
+    slot_t = torch.tensor(slot_ms + [0.0] * (4 - len(slot_ms)), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(slot_t, op=dist.ReduceOp.MAX)
+    slot_ms_max = [float(x) for x in slot_t.tolist()[:per_step]]
+    nominal = FP32_PEAK_NOMINAL_TF if args.precision != "float64" else FP32_PEAK_NOMINAL_TF / 2
+    traffic = None
+    if N == 1_000_000 and world == 1 and args.precision != "float64":
+        traffic = TRAFFIC_SYM_N1M if eng.symmetric else 33459712
     roofline = {
         "bound": "fp32" if args.precision != "float64" else "fp64",
-        "kernel": "nb::sweep_f32_kernel" if args.precision != "float64" else "nb::sweep_f64_kernel",
+        "kernel": kernel_name,
+        "algorithm": "pair-symmetric: each unordered pair evaluated once, applied to both particles" if eng.symmetric
+                     else "one-sided: every ordered pair evaluated",
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
         "peak_source": "FFMA (DFMA for float64) microbenchmark nb_ubench run in this process just before the timed "
                        "region; MEASURED_PEAKS.json carries no FP32/FP64 CUDA-core figure",
-        "peak_nominal": FP32_PEAK_NOMINAL_TF if args.precision != "float64" else FP32_PEAK_NOMINAL_TF / 2,
-        "frac_of_nominal": achieved_tf / (FP32_PEAK_NOMINAL_TF if args.precision != "float64" else FP32_PEAK_NOMINAL_TF / 2),
+        "peak_nominal": nominal, "frac_of_nominal": achieved_tf / nominal,
         "flops_per_interaction": FLOPS_PER_INTERACTION,
+        "note": "achieved = 20 flop x ordered pairs delivered / launch time (the reference's N^2 convention); the "
+                "symmetric sweep executes 16 packed FP32 instructions per two interactions where the one-sided "
+                "sweep executes 24, so its FP32-pipe utilisation (ncu, profiles/) is lower than this fraction",
         "launch_ms_avg": sweep_total_ms / max(1, len(sweep_ms)), "launches_timed": len(sweep_ms),
+        "launch_ms": [{"slot": k, "what": sweep_tags[k] if k < len(sweep_tags) else None, "ms_rank0": slot_ms[k],
+                       "ms_max_over_ranks": slot_ms_max[k]} for k in range(per_step)],
         "sweep_share_of_step": sweep_total_ms / elapsed_ms,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture of this
-        # command at the default workload (profiles/r01_ncu_sweep_f32_bench_n1m.md); null for other shapes
-        "traffic": 33459712 if (N == 1_000_000 and world == 1 and args.precision != "float64") else None,
-        "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic bytes per launch: 20 MB read + 32 MB "
-                        "partial sums written (absorbed by L2) for 2e13 algorithmic flop -> FP32-pipe bound",
+        # command at the default workload (profiles/); null for other shapes
+        "traffic": traffic,
+        "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic bytes per launch: 20 MB of records read "
+                        "+ 32 MB of double partial sums (L2-resident, atomically updated) for 2e13 algorithmic flop "
+                        "-> FP32-pipe bound",
     }
+
+    # ---- parity (outside the timed region): rank 0's first rows after the last step against the float64 oracle
+    parity = None
+    if args.parity_rows > 0:
+        xv_now = eng.state_numpy()                         # collective: every rank takes part
+        if rank == 0:
+            import oracle
+
+            oracle.build()
+            oracle.set_num_threads(len(os.sched_getaffinity(0)), fast=True)
+            R = int(min(args.parity_rows, eng.n_local))
+            p64 = xv_now[:, :3] if args.precision == "float64" else xv_now[:, :3].astype(np.float32).astype(np.float64)
+            m64 = float(m[0]) if args.precision == "float64" else float(np.float32(m[0]))
+            h64 = args.softening if args.precision == "float64" else float(np.float32(args.softening))
+            kwo = dict(kernel=args.kernel, rows=(0, R), fast=True)
+            a_ref = oracle.compute_nbody_forces_cpu(p64, m64, h64, nb.G_DEFAULT, **kwo)
+            p_ref = oracle.compute_nbody_potential_cpu(p64, m64, h64, nb.G_DEFAULT, **kwo)
+            a_gpu = eng.acc[:R].double().cpu().numpy()
+            p_gpu = eng.phi[:R].double().cpu().numpy()
+            rms = lambda x, r: float(np.sqrt(((x - r) ** 2).sum() / (r ** 2).sum()))  # noqa: E731
+            parity = {"acc_rel_rms": rms(a_gpu, a_ref), "phi_rel_rms": rms(p_gpu, p_ref),
+                      "acc_rel_max": float((np.linalg.norm(a_gpu - a_ref, axis=1) / np.linalg.norm(a_ref, axis=1)).max()),
+                      "rows": R, "tolerance": 1e-12 if args.precision == "float64" else 1e-5,
+                      "against": "float64 oracle (oracle/nbody_oracle.c) on the state after the last timed step"}
+            parity["ok"] = bool(max(parity["acc_rel_rms"], parity["phi_rel_rms"]) <= parity["tolerance"])
 
     # ---- e2e: public host-array API, H2D + D2H inside the timed region ----
     e2e = None
@@ -315,11 +394,9 @@ def main():
     if world == 1 and not args.skip_e2e:
         from nbody_streams_b200._lib import MODE_FORCE
 
-        sweeps = {}
-        for kname, mode, mname in (("plummer", MODE_FORCE, "force"), ("spline", MODE_FORCE, "force"),
-                                   ("spline", MODE_BOTH, "force+potential")):
+        def time_engine(kname, mode, algorithm):
             e = DirectEngine(N, float(m[0]), args.softening, prec, KERNEL_MAP[kname], nb.G_DEFAULT,
-                             EPS2_DEFAULT[args.precision], device)
+                             EPS2_DEFAULT[args.precision], device, algorithm=algorithm)
             e.load_state(xv)
             e.compute(mode, positions_changed=False)          # warm-up
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -328,10 +405,57 @@ def main():
                 e.compute(mode, positions_changed=False)
             a1.record()
             torch.cuda.synchronize()
-            ms = a0.elapsed_time(a1) / 2
-            sweeps[f"{kname}_{mname}"] = {"ms": ms, "interactions_per_s": float(N) * N / (ms * 1e-3),
-                                          "frac_of_measured_fp32_peak": float(N) * N / (ms * 1e-3) * 20 / 1e12 / peak_tf}
-            del e
+            return a0.elapsed_time(a1) / 2
+
+        sweeps = {}
+        for kname, mode, mname in (("plummer", MODE_FORCE, "force"), ("spline", MODE_FORCE, "force"),
+                                   ("spline", MODE_BOTH, "force+potential"), ("plummer", MODE_BOTH, "force+potential")):
+            for alg in ("symmetric", "onesided"):
+                if alg == "symmetric" and kname == args.kernel and mode == MODE_BOTH and eng.symmetric:
+                    continue                                      # that is the timed step itself
+                ms = time_engine(kname, mode, alg)
+                rate = float(N) * N / (ms * 1e-3)
+                sweeps[f"{kname}_{mname}_{alg}"] = {"ms": ms, "interactions_per_s": rate,
+                                                    "frac_of_nominal_peak": rate * 20 / 1e12 / nominal,
+                                                    "frac_of_measured_peak": rate * 20 / 1e12 / peak_tf}
+
+    # ---- the reference's own CUDA kernel on this GPU (cubins built from its templates, baseline/_ref) ----
+    ref_gpu = None
+    if world == 1 and not args.skip_ref_gpu and args.precision != "float64":
+        try:
+            sys.path.insert(0, str(ROOT / "tests"))
+            import ref_gpu_kernels as refk
+
+            if refk.available():
+                from nbody_streams_b200._lib import MODE_FORCE
+
+                n_ref = min(N, 262_144)
+                xr = torch.from_numpy(np.ascontiguousarray(xv[:n_ref, :3].astype(np.float32))).to(device)
+                mr = torch.full((n_ref,), float(m[0]), dtype=torch.float32, device=device)
+                hr = torch.full((n_ref,), args.softening, dtype=torch.float32, device=device)
+
+                def med(fn, reps=5, warm=2):               # the reference's protocol, fields.py:1291-1314
+                    ts = []
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    for r in range(warm + reps):
+                        torch.cuda.synchronize(); a0.record(); fn(); a1.record(); torch.cuda.synchronize()
+                        if r >= warm:
+                            ts.append(a0.elapsed_time(a1))
+                    return float(np.median(ts))
+
+                from nbody_streams_b200.fields import _run_direct
+
+                ref_gpu = {"n": n_ref, "precision": args.precision,
+                           "what": "reference nbody_forces(_kahan)_kernel_float4 (cuda_kernels.py), its flags, sm_100, "
+                                   "launch geometry of fields.py:823-852, kernel time only; ours = pack + sweep + finish"}
+                for kname in ("plummer", "spline"):
+                    kidr = KERNEL_MAP[kname]
+                    t_ref = med(lambda: refk.launch("force", args.precision, xr, mr, hr, nb.G_DEFAULT, kidr))
+                    t_our = med(lambda: _run_direct(xr, mr, 0.0, hr, 0.0, n_ref, prec, kidr, MODE_FORCE, nb.G_DEFAULT,
+                                                    EPS2_DEFAULT[args.precision], dtype_np))
+                    ref_gpu[f"force_{kname}"] = {"ref_ms": t_ref, "ours_ms": t_our, "speedup": t_ref / t_our}
+        except Exception as e:  # noqa: BLE001 - a missing cubin or cuda-python must not cost the bench line
+            ref_gpu = {"unavailable": repr(e)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -344,11 +468,14 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if args.precision != "float64" else "f64", "data": "synthetic",
-            "config": {
-                "workload": f"Plummer N={N} direct {args.precision} force+potential, kernel={args.kernel}, "
-                            f"softening={args.softening} (BASELINE config 3)",
-                "step": "KDK leapfrog step: fused kick+drift+repack, all-gather (N>1), one force+potential sweep "
-                        "over N^2 pairs, fix-up, half kick; float64 pos/vel resident on the device",
+            "config": config_dict(args, N),
+            "details": {
+                "algorithm": ("pair-symmetric sweep (nb::sym_*): every unordered pair evaluated once and applied to both "
+                              "particles, double atomics into a 32 B/particle workspace" if eng.symmetric else
+                              "one-sided sweep (nb::sweep_*): every ordered pair evaluated, bitwise reproducible"),
+                "step": "KDK leapfrog step: fused kick+drift+repack, all-gather of the j-records (N>1), one force+potential "
+                        "sweep delivering all N^2 interactions, reduce-scatter of the partial sums (N>1, symmetric), "
+                        "finish, half kick; float64 pos/vel resident on the device",
                 "parallelism": f"i-particles sharded over {world} GPU(s), j-records "
                                + ("pushed to all ranks by the fused kick+drift kernel over NVLink peer memory"
                                   if (world > 1 and args.exchange == "p2p") else "all-gathered over NCCL")
@@ -358,7 +485,7 @@ def main():
             },
             "fraction_of_fp32_peak": value * FLOPS_PER_INTERACTION / 1e12 / (peak_tf * world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
-            "other_sweeps": sweeps,
+            "parity": parity, "other_sweeps": sweeps, "ref_gpu_kernel": ref_gpu,
             "clocks": clocks,
         }
         print_json(line)

@@ -29,6 +29,10 @@ constexpr int SYM_NP          = 4;                       // packed i-pairs per t
 constexpr int SYM_IB_F32      = THREADS * 2 * SYM_NP;    // 1024 i-particles per CTA
 constexpr int SYM_TPB_F32     = SYM_IB_F32 / TJ;         // 4 tiles per i-block
 constexpr int SYM_FLUSH_TILES = 8;                       // i-side: float running sums -> double workspace
+#ifndef NB_SYM_UNROLL
+#define NB_SYM_UNROLL 4
+#endif
+constexpr int SYM_UNROLL = NB_SYM_UNROLL;                 // steps per iteration of the hot loop
 
 __device__ __forceinline__ f2 shfl2(const f2 v, const int src) {
     float lo, hi;
@@ -47,81 +51,6 @@ __device__ __forceinline__ float sum2(const f2 v) {
 struct JAcc32 {
     f2 x, y, z, p;
 };
-
-// ---------------------------------------------------------------------------
-// one (pair of i) x (one j) evaluation applied to both sides.
-//   U = true : i-block and j-tile have uniform mass and softening -> sums are unweighted (the masses are
-//              applied when the sums are folded / flushed) and cc = softening term of the pair
-//   U = false: general path, per-particle masses and max-softening rule per pair
-// ---------------------------------------------------------------------------
-template <int KID, int MODE, bool U>
-__device__ __forceinline__ void sym_pair_f32(const float xj, const float yj, const float zj, const float mj,
-                                             const float cj, const f2 xi, const f2 yi, const f2 zi, const f2 mi,
-                                             const float ci0, const float ci1, const f2 cc, f2& ax, f2& ay, f2& az,
-                                             f2& sp, JAcc32& J, const float eps2) {
-    const f2 dx = sub2(splat(xj), xi);
-    const f2 dy = sub2(splat(yj), yi);
-    const f2 dz = sub2(splat(zj), zi);
-    constexpr bool kUsesC = (KID == NB_KERNEL_PLUMMER || KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
-    constexpr bool kDehnen = (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
-    f2 h2, c;
-    if (KID == NB_KERNEL_NEWTONIAN) {
-        h2 = c = splat(eps2);
-    } else {
-        h2 = U ? cc : pk(fmaxf(cj, ci0), fmaxf(cj, ci1));
-        c  = kUsesC ? h2 : splat(eps2);
-    }
-    const f2 d = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, c)));
-    float d0, d1;
-    upk(d, d0, d1);
-    const f2 rinv  = pk(rsqrt_approx(d0), rsqrt_approx(d1));
-    const f2 rinv2 = mul2(rinv, rinv);
-    f2 w = 0ull, p = rinv;   // mass-less force factor (1/r^3-like) and potential factor (1/r-like)
-    if (kDehnen) {
-        const f2 t = mul2(add2(h2, splat(-eps2)), rinv2);   // c = h^2 + eps2 seeds the chain; the terms use bare h^2
-        if (MODE & NB_MODE_POT) {
-            const f2 pf = (KID == NB_KERNEL_DEHNEN_K1) ? fma2(splat(0.5f), t, splat(1.f))
-                                                       : fma2(t, fma2(splat(0.375f), t, splat(0.5f)), splat(1.f));
-            p = mul2(rinv, pf);
-        }
-        if (MODE & NB_MODE_FORCE) {
-            const f2 ff = (KID == NB_KERNEL_DEHNEN_K1) ? fma2(splat(1.5f), t, splat(1.f))
-                                                       : fma2(t, fma2(splat(3.75f), t, splat(1.5f)), splat(1.f));
-            w = mul2(mul2(rinv, rinv2), ff);
-        }
-    } else if (MODE & NB_MODE_FORCE) {
-        w = mul2(rinv, rinv2);
-    }
-    if (U) {
-        if (MODE & NB_MODE_POT) {
-            sp  = add2(sp, p);
-            J.p = add2(J.p, p);
-        }
-        if (MODE & NB_MODE_FORCE) {
-            ax  = fma2(w, dx, ax);
-            ay  = fma2(w, dy, ay);
-            az  = fma2(w, dz, az);
-            J.x = fma2(w, dx, J.x);
-            J.y = fma2(w, dy, J.y);
-            J.z = fma2(w, dz, J.z);
-        }
-    } else {
-        const f2 mjs = splat(mj);
-        if (MODE & NB_MODE_POT) {
-            sp  = fma2(mjs, p, sp);
-            J.p = fma2(mi, p, J.p);
-        }
-        if (MODE & NB_MODE_FORCE) {
-            const f2 fi = mul2(mjs, w), fj = mul2(mi, w);
-            ax  = fma2(fi, dx, ax);
-            ay  = fma2(fi, dy, ay);
-            az  = fma2(fi, dz, az);
-            J.x = fma2(fj, dx, J.x);
-            J.y = fma2(fj, dy, J.y);
-            J.z = fma2(fj, dz, J.z);
-        }
-    }
-}
 
 // exact cubic-spline evaluation of one scalar pair, both sides (the rare r < h case; reference
 // cuda_kernels.py:61-87 / :405-436 restated in spline_inside)
@@ -157,6 +86,15 @@ __device__ __forceinline__ void sym_spline_exact(const float xj, const float yj,
     }
 }
 
+// Hot per-thread i-state: positions and per-tile partial sums only.  The softening terms and masses of the
+// i-particles are needed by the rare paths only (general tiles, diagonal tiles, exact spline steps) and are
+// re-read from the packed records there, so they do not occupy registers in the hot loop.
+template <int NP>
+struct SymHot32 {
+    f2 x[NP], y[NP], z[NP];
+    f2 ax[NP], ay[NP], az[NP], sp[NP];
+};
+
 // thread state handed to the non-inlined cold paths (kept out of the hot loop's register allocation)
 template <int NP>
 struct SymCold32 {
@@ -164,6 +102,43 @@ struct SymCold32 {
     f2 m[NP];
     JAcc32 J;
 };
+
+// i-particle masses and softening terms of this thread's pairs, straight from the packed records
+// (dummy i beyond the i-range: massless)
+template <int NP>
+__device__ __forceinline__ void sym_load_mc(const unsigned char* __restrict__ packed, const long long ig0,
+                                            const long long i_end, SymCold32<NP>& T) {
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const long long ig = ig0 + 2LL * THREADS * q;
+        T.m[q] = 0ull;
+        T.S.c0[q] = T.S.c1[q] = 0.f;
+        if (ig < i_end) {
+            const long long t = ig / TJ;
+            const int kk      = static_cast<int>(ig - t * TJ);
+            const float* tb   = reinterpret_cast<const float*>(packed + static_cast<size_t>(t) * TILE_BYTES_F32);
+            T.m[q] = *reinterpret_cast<const f2*>(tb + COMP_M * TJ + kk);
+            const float2 c2 = *reinterpret_cast<const float2*>(tb + COMP_C * TJ + kk);
+            T.S.c0[q] = c2.x;
+            T.S.c1[q] = c2.y;
+        }
+    }
+}
+template <int NP>
+__device__ __forceinline__ void sym_hot_to_cold(const SymHot32<NP>& H, IState<NP>& S) {
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        S.x[q] = H.x[q]; S.y[q] = H.y[q]; S.z[q] = H.z[q];
+        S.ax[q] = H.ax[q]; S.ay[q] = H.ay[q]; S.az[q] = H.az[q]; S.sp[q] = H.sp[q];
+    }
+}
+template <int NP>
+__device__ __forceinline__ void sym_cold_to_hot(const IState<NP>& S, SymHot32<NP>& H) {
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        H.ax[q] = S.ax[q]; H.ay[q] = S.ay[q]; H.az[q] = S.az[q]; H.sp[q] = S.sp[q];
+    }
+}
 
 // the whole step (NP i-pairs x this lane's j) with the exact spline; U: unweighted sums
 template <int MODE, bool U, int NP>
@@ -187,18 +162,198 @@ __device__ __noinline__ void sym_spline_exact_step(SymCold32<NP>* T, const float
 }
 
 // ---------------------------------------------------------------------------
-// one symmetric j-tile against this thread's NP pairs; jw = this warp's slice [4][TJ] of the j-side buffer
+// one symmetric j-tile against this thread's NP pairs; jw = this warp's slice [4][TJ] of the j-side buffer.
+//   ST = SymHot32 (U: uniform fast path) or IState (general path; ci0/ci1/mi = per-particle terms)
+// The 256 steps of a tile (8 rounds x 32 rotation steps) form ONE software-pipelined loop: iteration t
+// finishes step t (kernel factors + accumulates from the separations and reciprocal square roots computed one
+// iteration earlier), rotates the j-accumulators, and then computes the separations, r^2 and MUFU.RSQ of step
+// t+1.  Neither the MUFU latency nor the LDS latency (records are fetched two steps ahead) nor the SHFL
+// latency (the rotation overlaps the next step's separations) sits on a dependency chain inside an
+// iteration — that matters because only 4 warps share an SM sub-partition at 128 registers per thread.
 // ---------------------------------------------------------------------------
-template <int KID, int MODE, bool U, int NP>
-__device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ stage, IState<NP>& S,
-                                             const f2 (&mi)[NP], const float cmax_i, const float c_pair,
-                                             const float eps2, float* __restrict__ jw, const int lane) {
+template <int KID, int MODE, bool U, int NP, typename ST>
+__device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ stage, ST& S, const f2* mi,
+                                             const float* ci0, const float* ci1, const float cmax_i,
+                                             const float c_pair, const float eps2, float* __restrict__ jw,
+                                             const int lane) {
     const float* __restrict__ sX = reinterpret_cast<const float*>(stage) + COMP_X * TJ;
     const float* __restrict__ sY = reinterpret_cast<const float*>(stage) + COMP_Y * TJ;
     const float* __restrict__ sZ = reinterpret_cast<const float*>(stage) + COMP_Z * TJ;
     const float* __restrict__ sM = reinterpret_cast<const float*>(stage) + COMP_M * TJ;
     const float* __restrict__ sC = reinterpret_cast<const float*>(stage) + COMP_C * TJ;
+    constexpr bool kUsesC  = (KID == NB_KERNEL_PLUMMER || KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
+    constexpr bool kDehnen = (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
     const f2 cc   = splat(c_pair);
+    const f2 ceps = splat(eps2);
+    const int src = (lane + 1) & 31;
+
+    // record of step t: particle 32 (t / 32) + (lane + t) mod 32 of the tile
+    auto rec_index = [&](int t) { return (t & (TJ - 32)) + ((lane + t) & 31); };
+    float xj, yj, zj, mj = 1.f, cj = c_pair;     // step t
+    float xn, yn, zn, mn = 1.f, cn = c_pair;     // step t + 1 (prefetched)
+    {
+        const int j0 = rec_index(0), j1 = rec_index(1);
+        xj = sX[j0]; yj = sY[j0]; zj = sZ[j0];
+        xn = sX[j1]; yn = sY[j1]; zn = sZ[j1];
+        if (!U) {
+            mj = sM[j0]; cj = sC[j0];
+            mn = sM[j1]; cn = sC[j1];
+        }
+    }
+    f2 dx[NP], dy[NP], dz[NP], rinv[NP], h2[NP];
+    bool exact = false;
+    // separations, softening term, r^2 and reciprocal square roots of the step whose record is (xj.., cj)
+    auto prepare = [&]() {
+        float dmin = 3.0e38f;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            dx[q] = sub2(splat(xj), S.x[q]);
+            dy[q] = sub2(splat(yj), S.y[q]);
+            dz[q] = sub2(splat(zj), S.z[q]);
+            f2 c;
+            if (KID == NB_KERNEL_NEWTONIAN) {
+                h2[q] = c = ceps;
+            } else {
+                h2[q] = U ? cc : pk(fmaxf(cj, ci0[q]), fmaxf(cj, ci1[q]));
+                c     = kUsesC ? h2[q] : ceps;
+            }
+            const f2 d = fma2(dx[q], dx[q], fma2(dy[q], dy[q], fma2(dz[q], dz[q], c)));
+            float d0, d1;
+            upk(d, d0, d1);
+            if (KID == NB_KERNEL_SPLINE) dmin = fminf(dmin, fminf(d0, d1));
+            rinv[q] = pk(rsqrt_approx(d0), rsqrt_approx(d1));
+        }
+        // the spline is exactly Newtonian unless some pair of the step lies inside its softening length
+        // (rare): then the whole step is redone with the reference's piecewise polynomial
+        if (KID == NB_KERNEL_SPLINE) exact = dmin < (U ? c_pair : fmaxf(cj, cmax_i));
+    };
+    prepare();
+
+    JAcc32 J;
+    J.x = J.y = J.z = J.p = 0ull;
+#pragma unroll SYM_UNROLL
+    for (int t = 0; t < TJ; ++t) {
+        if (exact) {
+            SymCold32<NP> T;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                T.S.x[q] = S.x[q]; T.S.y[q] = S.y[q]; T.S.z[q] = S.z[q];
+                T.S.ax[q] = S.ax[q]; T.S.ay[q] = S.ay[q]; T.S.az[q] = S.az[q]; T.S.sp[q] = S.sp[q];
+                T.S.c0[q] = U ? c_pair : ci0[q];
+                T.S.c1[q] = U ? c_pair : ci1[q];
+                T.m[q]    = U ? 0ull : mi[q];
+            }
+            T.J = J;
+            sym_spline_exact_step<MODE, U, NP>(&T, xj, yj, zj, mj, cj, eps2);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                S.ax[q] = T.S.ax[q]; S.ay[q] = T.S.ay[q]; S.az[q] = T.S.az[q]; S.sp[q] = T.S.sp[q];
+            }
+            J = T.J;
+        } else {
+            // kernel factors (mass-less: w ~ 1/r^3, p ~ 1/r) applied to both sides
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const f2 rinv2 = mul2(rinv[q], rinv[q]);
+                f2 w = 0ull, p = rinv[q];
+                if (kDehnen) {
+                    const f2 tt = mul2(add2(h2[q], splat(-eps2)), rinv2);   // the terms use the bare h^2
+                    if (MODE & NB_MODE_POT) {
+                        const f2 pf = (KID == NB_KERNEL_DEHNEN_K1)
+                                          ? fma2(splat(0.5f), tt, splat(1.f))
+                                          : fma2(tt, fma2(splat(0.375f), tt, splat(0.5f)), splat(1.f));
+                        p = mul2(rinv[q], pf);
+                    }
+                    if (MODE & NB_MODE_FORCE) {
+                        const f2 ff = (KID == NB_KERNEL_DEHNEN_K1)
+                                          ? fma2(splat(1.5f), tt, splat(1.f))
+                                          : fma2(tt, fma2(splat(3.75f), tt, splat(1.5f)), splat(1.f));
+                        w = mul2(mul2(rinv[q], rinv2), ff);
+                    }
+                } else if (MODE & NB_MODE_FORCE) {
+                    w = mul2(rinv[q], rinv2);
+                }
+                if (U) {
+                    if (MODE & NB_MODE_POT) {
+                        S.sp[q] = add2(S.sp[q], p);
+                        J.p     = add2(J.p, p);
+                    }
+                    if (MODE & NB_MODE_FORCE) {
+                        S.ax[q] = fma2(w, dx[q], S.ax[q]);
+                        S.ay[q] = fma2(w, dy[q], S.ay[q]);
+                        S.az[q] = fma2(w, dz[q], S.az[q]);
+                        J.x     = fma2(w, dx[q], J.x);
+                        J.y     = fma2(w, dy[q], J.y);
+                        J.z     = fma2(w, dz[q], J.z);
+                    }
+                } else {
+                    const f2 mjs = splat(mj);
+                    if (MODE & NB_MODE_POT) {
+                        S.sp[q] = fma2(mjs, p, S.sp[q]);
+                        J.p     = fma2(mi[q], p, J.p);
+                    }
+                    if (MODE & NB_MODE_FORCE) {
+                        const f2 fi = mul2(mjs, w), fj = mul2(mi[q], w);
+                        S.ax[q] = fma2(fi, dx[q], S.ax[q]);
+                        S.ay[q] = fma2(fi, dy[q], S.ay[q]);
+                        S.az[q] = fma2(fi, dz[q], S.az[q]);
+                        J.x     = fma2(fj, dx[q], J.x);
+                        J.y     = fma2(fj, dy[q], J.y);
+                        J.z     = fma2(fj, dz[q], J.z);
+                    }
+                }
+            }
+        }
+        // systolic rotation: the accumulators follow their j-particle to the lane that meets it next
+        if (MODE & NB_MODE_FORCE) {
+            J.x = shfl2(J.x, src);
+            J.y = shfl2(J.y, src);
+            J.z = shfl2(J.z, src);
+        }
+        if (MODE & NB_MODE_POT) J.p = shfl2(J.p, src);
+        if ((t & 31) == 31) {   // round complete: lane l holds the sums of particle (t - 31) + l
+            const int jb = t - 31;
+            if (MODE & NB_MODE_FORCE) {
+                jw[0 * TJ + jb + lane] = sum2(J.x);
+                jw[1 * TJ + jb + lane] = sum2(J.y);
+                jw[2 * TJ + jb + lane] = sum2(J.z);
+            }
+            if (MODE & NB_MODE_POT) jw[3 * TJ + jb + lane] = sum2(J.p);
+            J.x = J.y = J.z = J.p = 0ull;
+        }
+        // advance the record pipeline and prepare step t + 1 (the last iteration prepares a step that is not used)
+        xj = xn; yj = yn; zj = zn; mj = mn; cj = cn;
+        {
+            const int jn = rec_index((t + 2) & (TJ - 1));
+            xn = sX[jn]; yn = sY[jn]; zn = sZ[jn];
+            if (!U) {
+                mn = sM[jn];
+                cn = sC[jn];
+            }
+        }
+        prepare();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Cubic spline (the API default, sim.py:419): the same tile sweep, NOT software-pipelined.  A step computes
+// the separations and r^2 of its NP pairs and their minimum (one FMNMX3 per packed pair); the spline is
+// exactly Newtonian for r >= h (cuda_kernels.py:64-67), so unless that minimum lies below the largest
+// softening term that can apply the step finishes on the branch-free Newtonian path; otherwise (rare) the
+// whole step is redone by sym_spline_exact_step with the reference's piecewise polynomial.  The exact path
+// works on a copy of the thread state, which costs registers when several steps are in flight: measured best
+// with one step per iteration and the three phases in program order.
+// ---------------------------------------------------------------------------
+template <int MODE, bool U, int NP, typename ST>
+__device__ __forceinline__ void sym_tile_f32_spline(const unsigned char* __restrict__ stage, ST& S, const f2* mi,
+                                                    const float* ci0, const float* ci1, const float cmax_i,
+                                                    const float c_pair, const float eps2, float* __restrict__ jw,
+                                                    const int lane) {
+    const float* __restrict__ sX = reinterpret_cast<const float*>(stage) + COMP_X * TJ;
+    const float* __restrict__ sY = reinterpret_cast<const float*>(stage) + COMP_Y * TJ;
+    const float* __restrict__ sZ = reinterpret_cast<const float*>(stage) + COMP_Z * TJ;
+    const float* __restrict__ sM = reinterpret_cast<const float*>(stage) + COMP_M * TJ;
+    const float* __restrict__ sC = reinterpret_cast<const float*>(stage) + COMP_C * TJ;
     const f2 ceps = splat(eps2);
     const int src = (lane + 1) & 31;
 
@@ -207,86 +362,96 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
         JAcc32 J;
         J.x = J.y = J.z = J.p = 0ull;
         const int jb = 32 * rho;
-#pragma unroll 2
+        // the record of the NEXT step is fetched one step ahead (LDS latency off the critical path)
+        float xn = sX[jb + lane], yn = sY[jb + lane], zn = sZ[jb + lane], mn = 1.f, cn = c_pair;
+        if (!U) {
+            mn = sM[jb + lane];
+            cn = sC[jb + lane];
+        }
+#pragma unroll 1
         for (int s = 0; s < 32; ++s) {
-            const int jj   = jb + ((lane + s) & 31);
-            const float xj = sX[jj], yj = sY[jj], zj = sZ[jj];
-            float mj = 1.f, cj = c_pair;
-            if (!U) {
-                mj = sM[jj];
-                cj = sC[jj];
+            const float xj = xn, yj = yn, zj = zn, mj = mn, cj = cn;
+            {
+                const int jj = jb + ((lane + s + 1) & 31);   // s = 31 wraps to this lane's first record (unused)
+                xn = sX[jj];
+                yn = sY[jj];
+                zn = sZ[jj];
+                if (!U) {
+                    mn = sM[jj];
+                    cn = sC[jj];
+                }
             }
-            if (KID != NB_KERNEL_SPLINE) {
+            f2 dx[NP], dy[NP], dz[NP], d[NP];
+            float dmin = 3.0e38f;
 #pragma unroll
-                for (int q = 0; q < NP; ++q)
-                    sym_pair_f32<KID, MODE, U>(xj, yj, zj, mj, cj, S.x[q], S.y[q], S.z[q], mi[q], S.c0[q], S.c1[q], cc,
-                                               S.ax[q], S.ay[q], S.az[q], S.sp[q], J, eps2);
-            } else {
-                // two-phase: separations + r^2 and their minimum first; Newtonian finish unless some pair of
-                // the step may lie inside its softening length (then the step is redone exactly)
-                f2 dx[NP], dy[NP], dz[NP], d[NP];
-                float dmin = 3.0e38f;
+            for (int q = 0; q < NP; ++q) {
+                dx[q] = sub2(splat(xj), S.x[q]);
+                dy[q] = sub2(splat(yj), S.y[q]);
+                dz[q] = sub2(splat(zj), S.z[q]);
+                d[q]  = fma2(dx[q], dx[q], fma2(dy[q], dy[q], fma2(dz[q], dz[q], ceps)));
+                float d0, d1;
+                upk(d[q], d0, d1);
+                dmin = fminf(dmin, fminf(d0, d1));
+            }
+            if (dmin < (U ? c_pair : fmaxf(cj, cmax_i))) {
+                SymCold32<NP> T;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
-                    dx[q] = sub2(splat(xj), S.x[q]);
-                    dy[q] = sub2(splat(yj), S.y[q]);
-                    dz[q] = sub2(splat(zj), S.z[q]);
-                    d[q]  = fma2(dx[q], dx[q], fma2(dy[q], dy[q], fma2(dz[q], dz[q], ceps)));
+                    T.S.x[q] = S.x[q]; T.S.y[q] = S.y[q]; T.S.z[q] = S.z[q];
+                    T.S.ax[q] = S.ax[q]; T.S.ay[q] = S.ay[q]; T.S.az[q] = S.az[q]; T.S.sp[q] = S.sp[q];
+                    T.S.c0[q] = U ? c_pair : ci0[q];
+                    T.S.c1[q] = U ? c_pair : ci1[q];
+                    T.m[q]    = U ? 0ull : mi[q];
+                }
+                T.J = J;
+                sym_spline_exact_step<MODE, U, NP>(&T, xj, yj, zj, mj, cj, eps2);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    S.ax[q] = T.S.ax[q]; S.ay[q] = T.S.ay[q]; S.az[q] = T.S.az[q]; S.sp[q] = T.S.sp[q];
+                }
+                J = T.J;
+            } else {
+                f2 rinv[NP];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
                     float d0, d1;
                     upk(d[q], d0, d1);
-                    dmin = fminf(dmin, fminf(d0, d1));
+                    rinv[q] = pk(rsqrt_approx(d0), rsqrt_approx(d1));
                 }
-                const float h2lim = U ? c_pair : fmaxf(cj, cmax_i);
-                if (dmin < h2lim) {
-                    SymCold32<NP> T;
-                    T.S = S;
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) T.m[q] = mi[q];
-                    T.J = J;
-                    sym_spline_exact_step<MODE, U, NP>(&T, xj, yj, zj, mj, cj, eps2);
-                    S = T.S;
-                    J = T.J;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < NP; ++q) {
-                        float d0, d1;
-                        upk(d[q], d0, d1);
-                        const f2 rinv = pk(rsqrt_approx(d0), rsqrt_approx(d1));
-                        if (U) {
-                            if (MODE & NB_MODE_POT) {
-                                S.sp[q] = add2(S.sp[q], rinv);
-                                J.p     = add2(J.p, rinv);
-                            }
-                            if (MODE & NB_MODE_FORCE) {
-                                const f2 w = mul2(rinv, mul2(rinv, rinv));
-                                S.ax[q] = fma2(w, dx[q], S.ax[q]);
-                                S.ay[q] = fma2(w, dy[q], S.ay[q]);
-                                S.az[q] = fma2(w, dz[q], S.az[q]);
-                                J.x     = fma2(w, dx[q], J.x);
-                                J.y     = fma2(w, dy[q], J.y);
-                                J.z     = fma2(w, dz[q], J.z);
-                            }
-                        } else {
-                            const f2 mjs = splat(mj);
-                            if (MODE & NB_MODE_POT) {
-                                S.sp[q] = fma2(mjs, rinv, S.sp[q]);
-                                J.p     = fma2(mi[q], rinv, J.p);
-                            }
-                            if (MODE & NB_MODE_FORCE) {
-                                const f2 w  = mul2(rinv, mul2(rinv, rinv));
-                                const f2 fi = mul2(mjs, w), fj = mul2(mi[q], w);
-                                S.ax[q] = fma2(fi, dx[q], S.ax[q]);
-                                S.ay[q] = fma2(fi, dy[q], S.ay[q]);
-                                S.az[q] = fma2(fi, dz[q], S.az[q]);
-                                J.x     = fma2(fj, dx[q], J.x);
-                                J.y     = fma2(fj, dy[q], J.y);
-                                J.z     = fma2(fj, dz[q], J.z);
-                            }
+                for (int q = 0; q < NP; ++q) {
+                    const f2 w = (MODE & NB_MODE_FORCE) ? mul2(rinv[q], mul2(rinv[q], rinv[q])) : 0ull;
+                    if (U) {
+                        if (MODE & NB_MODE_POT) {
+                            S.sp[q] = add2(S.sp[q], rinv[q]);
+                            J.p     = add2(J.p, rinv[q]);
+                        }
+                        if (MODE & NB_MODE_FORCE) {
+                            S.ax[q] = fma2(w, dx[q], S.ax[q]);
+                            S.ay[q] = fma2(w, dy[q], S.ay[q]);
+                            S.az[q] = fma2(w, dz[q], S.az[q]);
+                            J.x     = fma2(w, dx[q], J.x);
+                            J.y     = fma2(w, dy[q], J.y);
+                            J.z     = fma2(w, dz[q], J.z);
+                        }
+                    } else {
+                        const f2 mjs = splat(mj);
+                        if (MODE & NB_MODE_POT) {
+                            S.sp[q] = fma2(mjs, rinv[q], S.sp[q]);
+                            J.p     = fma2(mi[q], rinv[q], J.p);
+                        }
+                        if (MODE & NB_MODE_FORCE) {
+                            const f2 fi = mul2(mjs, w), fj = mul2(mi[q], w);
+                            S.ax[q] = fma2(fi, dx[q], S.ax[q]);
+                            S.ay[q] = fma2(fi, dy[q], S.ay[q]);
+                            S.az[q] = fma2(fi, dz[q], S.az[q]);
+                            J.x     = fma2(fj, dx[q], J.x);
+                            J.y     = fma2(fj, dy[q], J.y);
+                            J.z     = fma2(fj, dz[q], J.z);
                         }
                     }
                 }
             }
-            // systolic rotation: the accumulators follow their j-particle to the lane that meets it next
             if (MODE & NB_MODE_FORCE) {
                 J.x = shfl2(J.x, src);
                 J.y = shfl2(J.y, src);
@@ -294,7 +459,6 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
             }
             if (MODE & NB_MODE_POT) J.p = shfl2(J.p, src);
         }
-        // after 32 rotations lane l holds the sums of particle jb + l
         if (MODE & NB_MODE_FORCE) {
             jw[0 * TJ + jb + lane] = sum2(J.x);
             jw[1 * TJ + jb + lane] = sum2(J.y);
@@ -304,17 +468,47 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
     }
 }
 
+// kernel-id dispatch of the two loop styles
+template <int KID, int MODE, bool U, int NP, typename ST>
+__device__ __forceinline__ void sym_tile_f32_any(const unsigned char* __restrict__ stage, ST& S, const f2* mi,
+                                                 const float* ci0, const float* ci1, const float cmax_i,
+                                                 const float c_pair, const float eps2, float* __restrict__ jw,
+                                                 const int lane) {
+    if constexpr (KID == NB_KERNEL_SPLINE)
+        sym_tile_f32_spline<MODE, U, NP, ST>(stage, S, mi, ci0, ci1, cmax_i, c_pair, eps2, jw, lane);
+    else
+        sym_tile_f32<KID, MODE, U, NP, ST>(stage, S, mi, ci0, ci1, cmax_i, c_pair, eps2, jw, lane);
+}
+
 // general (per-particle mass / softening) symmetric tile: rare (species boundaries, per-particle softening
-// arrays, padding) -> non-inlined on a copy of the state, like the masked tile of the one-sided sweep
+// arrays, padding) -> non-inlined, re-reads the i-particles' masses and softening terms from the packed
+// records and works on a copy of the hot state
 template <int KID, int MODE, int NP>
-__device__ __noinline__ void sym_tile_f32_general(const unsigned char* stage, SymCold32<NP>* T, const float cmax_i,
-                                                  const float eps2, float* jw, const int lane) {
-    IState<NP> S = T->S;   // work on registers, not on the caller's local-memory copy
-    f2 m[NP];
+__device__ __noinline__ void sym_tile_f32_general(const unsigned char* stage, SymHot32<NP>* H,
+                                                  const unsigned char* packed, const long long ig0,
+                                                  const long long i_end, const float eps2, float* jw,
+                                                  const int lane) {
+    SymCold32<NP> T;
+    sym_hot_to_cold<NP>(*H, T.S);
+    sym_load_mc<NP>(packed, ig0, i_end, T);
+    float cmax_i = 0.f;
 #pragma unroll
-    for (int q = 0; q < NP; ++q) m[q] = T->m[q];
-    sym_tile_f32<KID, MODE, false, NP>(stage, S, m, cmax_i, 0.f, eps2, jw, lane);
-    T->S = S;
+    for (int q = 0; q < NP; ++q) cmax_i = fmaxf(cmax_i, fmaxf(T.S.c0[q], T.S.c1[q]));
+    sym_tile_f32_any<KID, MODE, false, NP, IState<NP>>(stage, T.S, T.m, T.S.c0, T.S.c1, cmax_i, 0.f, eps2, jw, lane);
+    sym_cold_to_hot<NP>(T.S, *H);
+}
+
+// diagonal tile (overlaps the CTA's own i-block): one-sided masked path of nb_sweep_f32.cuh
+template <int KID, int MODE, int NP>
+__device__ __noinline__ void sym_tile_f32_diag(const unsigned char* stage, SymHot32<NP>* H,
+                                               const unsigned char* packed, const long long ig0,
+                                               const long long i_end, const float eps2, const long long jg0,
+                                               const long long n_j) {
+    SymCold32<NP> T;
+    sym_hot_to_cold<NP>(*H, T.S);
+    sym_load_mc<NP>(packed, ig0, i_end, T);
+    tile_f32<KID, MODE, true, false, false, NP, 4>(stage, T.S, eps2, 0.f, jg0, ig0, n_j);
+    sym_cold_to_hot<NP>(T.S, *H);
 }
 
 template <int NP>
@@ -412,16 +606,12 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
         const int tile0          = a.it0 + TPB * ib;
         const long long ig_block = static_cast<long long>(tile0) * TJ;
         const long long ig0      = ig_block + 2LL * tid;
-        IState<NP> S;
-        f2 mi[NP];
-        float cmax_i = 0.f;
+        SymHot32<NP> S;
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             const long long ig = ig0 + 2LL * THREADS * q;   // even; ig+1 is in the same tile
-            // dummy i beyond the i-range: far away and massless -> contributes nothing, results discarded
+            // dummy i beyond the i-range: far away (and massless, see sym_load_mc) -> contributes nothing
             S.x[q] = S.y[q] = S.z[q] = splat(NB_PAD_POS_F32);
-            S.c0[q] = S.c1[q] = 0.f;
-            mi[q] = 0ull;
             if (ig < i_end) {
                 const long long t = ig / TJ;
                 const int kk      = static_cast<int>(ig - t * TJ);
@@ -429,12 +619,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
                 S.x[q] = *reinterpret_cast<const f2*>(tb + COMP_X * TJ + kk);
                 S.y[q] = *reinterpret_cast<const f2*>(tb + COMP_Y * TJ + kk);
                 S.z[q] = *reinterpret_cast<const f2*>(tb + COMP_Z * TJ + kk);
-                mi[q]  = *reinterpret_cast<const f2*>(tb + COMP_M * TJ + kk);
-                const float2 c2 = *reinterpret_cast<const float2*>(tb + COMP_C * TJ + kk);
-                S.c0[q] = c2.x;
-                S.c1[q] = c2.y;
             }
-            cmax_i = fmaxf(cmax_i, fmaxf(S.c0[q], S.c1[q]));
             S.ax[q] = S.ay[q] = S.az[q] = S.sp[q] = 0ull;
         }
         // is the whole i-block one species (same mass and softening, no padding, all TPB tiles present)?
@@ -490,23 +675,18 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
             const float4 meta = *reinterpret_cast<const float4*>(stage + 5 * TJ * 4);   // {c_uni|NaN, m_uni|NaN, c_max, -}
             float m_fold = 1.f;
             if (diag) {
-                IState<NP> T = S;
-                tile_f32_masked<KID, MODE, NP, 4>(stage, &T, eps2, static_cast<long long>(gt) * TJ, ig0, a.n_j);
-                S = T;
+                sym_tile_f32_diag<KID, MODE, NP>(stage, &S, a.packed, ig0, i_end, eps2, static_cast<long long>(gt) * TJ,
+                                                 a.n_j);
             } else {
                 float* jw = jbuf + warp * 4 * TJ;
                 if (blk_uni && meta.x == meta.x && meta.y == meta.y) {
                     m_fold     = meta.y;
                     pend_scale = mI;
-                    sym_tile_f32<KID, MODE, true, NP>(stage, S, mi, cmax_i, fmaxf(cI, meta.x), eps2, jw, lane);
+                    sym_tile_f32_any<KID, MODE, true, NP, SymHot32<NP>>(stage, S, nullptr, nullptr, nullptr, 0.f,
+                                                                         fmaxf(cI, meta.x), eps2, jw, lane);
                 } else {
                     pend_scale = 1.f;
-                    SymCold32<NP> T;
-                    T.S = S;
-#pragma unroll
-                    for (int q = 0; q < NP; ++q) T.m[q] = mi[q];
-                    sym_tile_f32_general<KID, MODE, NP>(stage, &T, cmax_i, eps2, jw, lane);
-                    S = T.S;
+                    sym_tile_f32_general<KID, MODE, NP>(stage, &S, a.packed, ig0, i_end, eps2, jw, lane);
                 }
                 pend    = true;
                 pend_gt = gt;

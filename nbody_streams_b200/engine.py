@@ -77,6 +77,51 @@ class ShardLayout:
         return slice(f, f + self.count(rank))
 
 
+def sym_plan(layout: ShardLayout, rank: int, tpb: int) -> dict:
+    """Tile ranges one rank sweeps with the pair-symmetric kernel so that, over all ranks, every unordered
+    pair of particles is evaluated exactly once (``nb_sym_sweep`` arguments, see include/nbody_sm100.h).
+
+    Shards form a ring: rank r takes the pairs inside its own shard (``tri``) and the full rectangles
+    (own shard) x (shard r+k), k = 1..(G-1)//2, as up to two contiguous tile ranges A and B (wrap-around).
+    For an even ring the opposite shard o = r + G/2 is shared: the lower rank sweeps its FIRST half of
+    i-blocks against all of shard o (range C restricted to i-blocks [0, h)), the upper rank sweeps all of
+    its i-blocks against the tiles of the SECOND half of the lower rank's shard (range C, all i-blocks).
+    All-padding tiles (>= layout.tiles_total) are never swept.  Pure Python: tested on CPU."""
+    G, T, R = layout.world, layout.tiles_per_rank, layout.tiles_total
+
+    def shard(s):
+        b = min(s * T, R)
+        return b, min((s + 1) * T, R)
+
+    own = shard(rank)
+    n_ib = (own[1] - own[0] + tpb - 1) // tpb
+    plan = {"own": own, "n_ib": n_ib, "A": (0, 0), "B": (0, 0), "C": (0, 0), "ibC": (0, 0)}
+    K = (G - 1) // 2
+    if K > 0:
+        first, last = rank + 1, rank + K                       # shards first..last (mod G), contiguous on the ring
+        if last < G:
+            plan["A"] = (shard(first)[0], shard(last)[1])
+        elif first >= G:
+            plan["A"] = (shard(first - G)[0], shard(last - G)[1])
+        else:
+            plan["A"] = (shard(first)[0], shard(G - 1)[1])
+            plan["B"] = (shard(0)[0], shard(last - G)[1])
+    if G % 2 == 0 and G > 1:
+        half = G // 2
+        if rank < half:
+            plan["C"] = shard(rank + half)
+            plan["ibC"] = (0, n_ib // 2)
+        else:
+            lo = shard(rank - half)
+            n_ib_lo = (lo[1] - lo[0] + tpb - 1) // tpb
+            plan["C"] = (min(lo[0] + (n_ib_lo // 2) * tpb, lo[1]), lo[1])
+            plan["ibC"] = (0, n_ib)
+    for k in ("A", "B", "C"):
+        if plan[k][1] <= plan[k][0]:
+            plan[k] = (0, 0)
+    return plan
+
+
 def _dist():
     import torch.distributed as dist
 
@@ -102,6 +147,18 @@ def allgather_shards(buf, layout: ShardLayout, rank: int, shard_bytes: int, grou
     return _dist().all_gather_into_tensor(out, inp, group=group)
 
 
+def reduce_scatter_shards(ws, out, layout: ShardLayout, rank: int, group=None):
+    """out (shard rows) = sum over ranks of rows [rank*shard, (rank+1)*shard) of ws (n_slots rows).
+    NCCL: one reduce-scatter; backends without it (gloo, CPU tests): all-reduce + slice."""
+    dist = _dist()
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(out, ws, group=group)
+    else:
+        dist.all_reduce(ws, group=group)
+        out.copy_(ws[rank * layout.shard:(rank + 1) * layout.shard])
+    return out
+
+
 def gather_rows(local, layout: ShardLayout, rank: int, group=None):
     """All ranks receive the (N, k) concatenation of every rank's real rows."""
     import torch
@@ -115,6 +172,29 @@ def gather_rows(local, layout: ShardLayout, rank: int, group=None):
     _dist().all_gather_into_tensor(out, padded, group=group)
     out = out[: layout.N]
     return out if local.dim() > 1 else out.reshape(-1)
+
+
+def gather_rows_padded(padded, layout: ShardLayout, rank: int, group=None, root_only: bool = False, local=None):
+    """Gather shard-sized (padded) row blocks WITHOUT a staging copy: `padded` has layout.shard rows of which the
+    first layout.count(rank) are real.  All ranks (or only rank 0 with root_only; the others get `local` back)
+    receive the first N rows of the concatenation."""
+    import torch
+
+    if layout.world == 1:
+        return padded[: layout.N]
+    dist = _dist()
+    shape = (layout.n_slots,) + tuple(padded.shape[1:])
+    if root_only:
+        root = dist.get_global_rank(group, 0) if group is not None else 0
+        if rank == 0:
+            out = torch.empty(shape, dtype=padded.dtype, device=padded.device)
+            dist.gather(padded, list(out.split(layout.shard)), dst=root, group=group)
+            return out[: layout.N]
+        dist.gather(padded, None, dst=root, group=group)
+        return local if local is not None else padded[: layout.count(rank)]
+    out = torch.empty(shape, dtype=padded.dtype, device=padded.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return out[: layout.N]
 
 
 # ---------------------------------------------------------------------------
@@ -135,6 +215,10 @@ class DirectEngine:
                kick+drift kernel stores the refreshed records straight into every rank's buffer over
                NVLink (NVSwitch multicast when available, else one store per peer), bracketed by
                symmetric-memory barriers: no separate collective runs.
+    algorithm : None/'auto' (pair-symmetric sweep from nb_sym_min_n() particles on), 'symmetric', 'onesided'.
+              With the symmetric sweep on several ranks each rank evaluates 1/world of the unordered pairs
+              (ring schedule, `sym_plan`) into partial sums for ALL particles it touched, and a
+              reduce-scatter (NCCL, double) delivers every shard's sums to its owner.
     overlap : sweep the local j-shard while the all-gather is in flight (default);
               False sweeps all tiles in global (j-ascending) order after the gather.
               Either way results are bitwise reproducible for a given rank count and agree
@@ -142,7 +226,7 @@ class DirectEngine:
     """
 
     def __init__(self, N, mass, softening, prec, kernel_id, G, eps2, device, group=None, overlap=True,
-                 exchange="nccl"):
+                 exchange="nccl", algorithm=None):
         torch = _lib.require_cuda()
         self.torch = torch
         self.lib = _lib.load()
@@ -154,6 +238,13 @@ class DirectEngine:
         self.rank, self.world = group_info(group)
         self.overlap = bool(overlap) and self.world > 1
         self.layout = ShardLayout(self.N, self.world)
+        from .fields import use_symmetric
+
+        # pair-symmetric sweep (every unordered pair once, partial sums of BOTH particles; large N) or the
+        # one-sided sweep (bitwise reproducible, finer work units; small N)
+        self.symmetric = use_symmetric(self.N, algorithm)
+        self._sym_ws = None
+        self._sym_out = None
         self.first = self.layout.first(self.rank)
         self.n_local = self.layout.count(self.rank)
         self.shard_bytes = int(self.lib.nb_packed_bytes(self.prec, self.layout.shard))
@@ -224,6 +315,87 @@ class DirectEngine:
         m = np.asarray(self._mass_host[self.layout.rows(self.rank)], dtype=np.float64)
         return torch.from_numpy(np.ascontiguousarray(m)).to(self.device)
 
+    def _sym_grid(self, mode):
+        g = self._grids.get(("sym", mode))
+        if g is None:
+            out = C.c_int(0)
+            with self.torch.cuda.device(self.device):
+                _lib.check(self.lib.nb_sym_grid(self.prec, self.kernel_id, mode, C.byref(out)))
+            g = self._grids[("sym", mode)] = int(out.value)
+        return g
+
+    def _sym_buffers(self):
+        """Workspace of 4 doubles per particle slot (all shards) + this rank's reduce-scatter output."""
+        torch = self.torch
+        if self._sym_ws is None:
+            self._sym_ws = torch.zeros((self.layout.n_slots, 4), dtype=torch.float64, device=self.device)
+            if self.world > 1:
+                self._sym_out = torch.zeros((self.layout.shard, 4), dtype=torch.float64, device=self.device)
+        return self._sym_ws, self._sym_out
+
+    def _sym_sweep(self, mode, plan, tri, rect, zero_first, grid, ws):
+        """One nb_sym_sweep launch: the triangle of the own shard and/or the rectangle ranges of `plan`."""
+        torch = self.torch
+        A, B, Cr, ibC = (plan["A"], plan["B"], plan["C"], plan["ibC"]) if rect else ((0, 0),) * 4
+        own = plan["own"]
+        ev = None
+        if self.sweep_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(self.device))
+        _lib.check(self.lib.nb_sym_sweep(self.prec, self.kernel_id, mode, self.packed.data_ptr(), self.N,
+                                         own[0], own[1], 1 if tri else 0, A[0], A[1], B[0], B[1], Cr[0], Cr[1],
+                                         ibC[0], ibC[1], self.eps2, ws.data_ptr(), ws.numel() * 8,
+                                         self.layout.n_slots, 1 if zero_first else 0, grid, self._stream()))
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(self.device))
+            self.sweep_events.append((ev[0], ev[1], "tri" if tri and not rect else ("rect" if rect and not tri else "all")))
+        self.launches += 1 + (1 if zero_first else 0)
+
+    def _compute_sym(self, mode, positions_changed):
+        torch, lib = self.torch, self.lib
+        grid = self._sym_grid(mode)
+        ws, out = self._sym_buffers()
+        plan = sym_plan(self.layout, self.rank, lib.nb_sym_block_tiles(self.prec))
+        has_own = plan["own"][1] > plan["own"][0]
+        has_rect = has_own and any(plan[k][1] > plan[k][0] for k in ("A", "B", "C"))
+        p2p = self.exchange == "p2p"
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            if self.world > 1 and positions_changed and not p2p:
+                self.comm_stream.wait_stream(cur)          # shard records are written on `cur`
+                with torch.cuda.stream(self.comm_stream):
+                    allgather_shards(self.packed, self.layout, self.rank, self.shard_bytes, self.group)
+
+            def wait_exchange():
+                if self.world == 1:
+                    return
+                if p2p:
+                    if positions_changed:
+                        self._symm.barrier(channel=1)      # every rank's pushed records have landed
+                else:
+                    cur.wait_stream(self.comm_stream)
+
+            if not has_own:
+                ws.zero_()
+                wait_exchange()
+            elif self.overlap:
+                self._sym_sweep(mode, plan, True, False, True, grid, ws)      # own shard: no dependency
+                wait_exchange()
+                if has_rect:
+                    self._sym_sweep(mode, plan, False, True, False, grid, ws)
+            else:
+                wait_exchange()
+                self._sym_sweep(mode, plan, True, has_rect, True, grid, ws)
+            src, first = ws, self.first
+            if self.world > 1:
+                reduce_scatter_shards(ws, out, self.layout, self.rank, self.group)   # my shard's sums from every rank
+                src, first = out, 0
+            if self.n_local > 0:
+                _lib.check(lib.nb_sym_finish(self.prec, mode, src.data_ptr(), first, self.n_local, self.G,
+                                             self.acc.data_ptr() if mode & MODE_FORCE else None,
+                                             self.phi.data_ptr() if mode & MODE_POT else None, self._stream()))
+                self.launches += 1
+
     def _grid(self, mode):
         g = self._grids.get(mode)
         if g is None:
@@ -293,6 +465,8 @@ class DirectEngine:
         """Sweep + finish into self.acc / self.phi for this rank's i-particles.
         Assumes the packed records of this rank's shard are current; all-gathers them
         first when world > 1 and `positions_changed`."""
+        if self.symmetric:
+            return self._compute_sym(mode, positions_changed)
         torch, lib = self.torch, self.lib
         grid = self._grid(mode)
         ws = self._workspace(grid)
@@ -381,8 +555,12 @@ class DirectEngine:
         with torch.cuda.device(self.device):
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
-            self._grid(mode)
-            self._workspace(self._grid(mode))          # allocate outside the capture
+            if self.symmetric:
+                self._sym_grid(mode)
+                self._sym_buffers()
+            else:
+                self._grid(mode)
+                self._workspace(self._grid(mode))      # allocate outside the capture
             graph = torch.cuda.CUDAGraph()
             saved_events, self.sweep_events = self.sweep_events, None
             with torch.cuda.graph(graph, stream=side):
@@ -390,7 +568,7 @@ class DirectEngine:
                 self.compute(mode)
                 self.kick(dt)
             self.sweep_events = saved_events
-        per_step = 4
+        per_step = 5 if self.symmetric else 4        # the symmetric sweep is preceded by a memset node
 
         def replay():
             graph.replay()
@@ -419,4 +597,4 @@ class DirectEngine:
         return out.cpu().numpy()
 
 
-__all__ = ["ShardLayout", "DirectEngine", "allgather_shards", "gather_rows", "group_info", "TILE_J"]
+__all__ = ["ShardLayout", "DirectEngine", "sym_plan", "reduce_scatter_shards", "gather_rows_padded", "allgather_shards", "gather_rows", "group_info", "TILE_J"]

@@ -244,41 +244,70 @@ def _device_operand(arr_cpu, scalar, original, dtype_t, device):
     return t.contiguous(), 0.0
 
 
+def _to_host(t):
+    """Device tensor -> NumPy through page-locked memory: one asynchronous copy at PCIe speed instead of the
+    staged pageable path of ``Tensor.cpu()`` (the array owns its pinned block, which returns to torch's caching
+    host allocator when the array dies).  Falls back to ``.cpu()`` where pinning is unavailable."""
+    import torch
+
+    t = t.as_subclass(torch.Tensor)
+    if t.numel() == 0:
+        return t.cpu().numpy()
+    try:
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:
+        return t.cpu().numpy()
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return out.numpy()
+
+
 def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, mode, G, eps2, dtype_np, group=None,
-                n_sources=None, algorithm=None):
+                n_sources=None, algorithm=None, gather="all"):
     """pack + sweep + finish on the current stream.  Returns (acc|None, phi|None) torch tensors.
 
-    With a torch.distributed `group` of more than one rank every rank packs all N particles, sweeps only
-    the i-rows of its tile-aligned shard and the rows are all-gathered, so each rank returns full arrays.
+    With a torch.distributed `group` of more than one rank every rank packs all N particles and evaluates its
+    share of the pair work: with the pair-symmetric sweep 1/world of the unordered pairs (ring schedule,
+    engine.sym_plan) followed by a reduce-scatter of the partial sums, with the one-sided sweep the i-rows of
+    its tile-aligned shard.  `gather`: 'all' (default) — the rows are all-gathered and every rank returns the
+    full arrays; 'root' — only rank 0 of the group receives them (the others return their own rows);
+    'local' — no gather, every rank returns the rows of its shard (``ShardLayout(N, world).rows(rank)``).
 
     `n_sources` (None = N): only the j-tiles holding particles [0, n_sources) are swept, i.e. the first
     n_sources particles are the sources and all N are targets.  The caller passes zero masses for the
     particles >= n_sources (the tile straddling n_sources is swept whole)."""
     import torch
 
-    from .engine import ShardLayout, gather_rows, group_info
+    from .engine import ShardLayout, gather_rows_padded, group_info, reduce_scatter_shards, sym_plan
 
+    if gather not in ("all", "root", "local"):
+        raise ValueError(f"gather must be 'all', 'root' or 'local', got {gather!r}")
     lib = _lib.load()
     device = pos_t.device
     dtype_t = _np_to_torch_dtype(dtype_np)
     rank, world = group_info(group) if group is not None else (0, 1)
     layout = ShardLayout(N, world)
     i_begin, n_i = layout.first(rank), layout.count(rank)
-    acc = torch.empty((n_i, 3), dtype=dtype_t, device=device) if mode & MODE_FORCE else None
-    phi = torch.empty((n_i,), dtype=dtype_t, device=device) if mode & MODE_POT else None
+    # multi-rank: outputs are allocated shard-sized (padded) so the all-gather needs no staging copy
+    n_rows = layout.shard if world > 1 else n_i
+    acc_buf = torch.empty((n_rows, 3), dtype=dtype_t, device=device) if mode & MODE_FORCE else None
+    phi_buf = torch.empty((n_rows,), dtype=dtype_t, device=device) if mode & MODE_POT else None
+    acc = acc_buf[:n_i] if acc_buf is not None else None
+    phi = phi_buf[:n_i] if phi_buf is not None else None
     if N == 0:
         return acc, phi
+    sym = n_sources is None and use_symmetric(N, algorithm)
     with torch.cuda.device(device):
-        grid = _grid_for(prec, kernel_id, mode, device)
-        packed = _scratch(device, "packed", lib.nb_packed_bytes(prec, N))
+        grid = _grid_for(prec, kernel_id, mode, device, sym=sym)
+        n_slots = layout.n_slots if world > 1 else lib.nb_padded_count(N)
+        packed = _scratch(device, "packed", lib.nb_packed_bytes(prec, n_slots))
         stream = torch.cuda.current_stream(device).cuda_stream
         mass_ptr, mass_dt = (mass_t.data_ptr(), _dt_code(mass_t)) if mass_t is not None else (None, 0)
         h_ptr, h_dt = (h_t.data_ptr(), _dt_code(h_t)) if h_t is not None else (None, 0)
-        acc_ptr = acc.data_ptr() if acc is not None else None
-        phi_ptr = phi.data_ptr() if phi is not None else None
-        if world == 1 and n_sources is None and use_symmetric(N, algorithm):
-            grid = _grid_for(prec, kernel_id, mode, device, sym=True)
-            ws_bytes = lib.nb_sym_workspace_bytes(lib.nb_padded_count(N))
+        acc_ptr = acc_buf.data_ptr() if acc_buf is not None else None
+        phi_ptr = phi_buf.data_ptr() if phi_buf is not None else None
+        if world == 1 and sym:
+            ws_bytes = lib.nb_sym_workspace_bytes(n_slots)
             ws = _scratch(device, "workspace", ws_bytes)
             _lib.check(lib.nb_direct_sym(prec, kernel_id, mode, pos_t.data_ptr(), _dt_code(pos_t), mass_ptr, mass_dt,
                                          float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, float(G), float(eps2),
@@ -290,11 +319,28 @@ def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, m
                                      float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, float(G), float(eps2),
                                      packed.data_ptr(), ws.data_ptr(), ws_bytes, grid, acc_ptr, phi_ptr, stream))
         else:
-            n_pad = lib.nb_padded_count(N)
             _lib.check(lib.nb_pack(prec, kernel_id, packed.data_ptr(), 0, pos_t.data_ptr(), _dt_code(pos_t),
-                                   mass_ptr, mass_dt, float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, n_pad,
+                                   mass_ptr, mass_dt, float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, n_slots,
                                    float(eps2), stream))
-            if n_i > 0:
+            if sym:
+                ws_bytes = lib.nb_sym_workspace_bytes(n_slots)
+                ws = _scratch(device, "workspace", ws_bytes)
+                ws_rows = ws[:ws_bytes].view(torch.float64).view(n_slots, 4)
+                plan = sym_plan(layout, rank, lib.nb_sym_block_tiles(prec))
+                own = plan["own"]
+                if own[1] > own[0]:
+                    A, B, Cr, ibC = plan["A"], plan["B"], plan["C"], plan["ibC"]
+                    _lib.check(lib.nb_sym_sweep(prec, kernel_id, mode, packed.data_ptr(), N, own[0], own[1], 1,
+                                                A[0], A[1], B[0], B[1], Cr[0], Cr[1], ibC[0], ibC[1], float(eps2),
+                                                ws.data_ptr(), ws_bytes, n_slots, 1, grid, stream))
+                else:
+                    ws_rows.zero_()
+                mine = torch.empty((layout.shard, 4), dtype=torch.float64, device=device)
+                reduce_scatter_shards(ws_rows, mine, layout, rank, group)
+                if n_i > 0:
+                    _lib.check(lib.nb_sym_finish(prec, mode, mine.data_ptr(), 0, n_i, float(G), acc_ptr, phi_ptr,
+                                                 stream))
+            elif n_i > 0:
                 ws_bytes = lib.nb_workspace_bytes(prec, n_i, grid, 1)
                 ws = _scratch(device, "workspace", ws_bytes)
                 n_src = N if n_sources is None else max(0, min(int(n_sources), N))
@@ -303,11 +349,11 @@ def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, m
                                         i_begin, n_i, float(eps2), ws.data_ptr(), ws_bytes, 0, grid, stream))
                 _lib.check(lib.nb_finish(prec, kernel_id, mode, n_i, grid, 1, C.byref(n_tiles), ws.data_ptr(),
                                          float(G), acc_ptr, phi_ptr, stream))
-            if world > 1:
-                if acc is not None:
-                    acc = gather_rows(acc, layout, rank, group)
-                if phi is not None:
-                    phi = gather_rows(phi, layout, rank, group)
+            if world > 1 and gather != "local":
+                if acc_buf is not None:
+                    acc = gather_rows_padded(acc_buf, layout, rank, group, root_only=(gather == "root"), local=acc)
+                if phi_buf is not None:
+                    phi = gather_rows_padded(phi_buf, layout, rank, group, root_only=(gather == "root"), local=phi)
     return acc, phi
 
 
@@ -382,6 +428,7 @@ def compute_nbody_forces_gpu(
     group=None,
     n_sources=None,
     algorithm=None,
+    gather="all",
 ):
     """Direct-summation gravitational accelerations on the GPU.
 
@@ -402,7 +449,9 @@ def compute_nbody_forces_gpu(
     ``n_sources`` makes only the first n_sources particles gravitating sources
     (the others are massless test particles and their source tiles are never
     swept: N x n_sources pair work, used by ``unbind.iterative_unbinding``),
-    ``algorithm`` ('auto' | 'symmetric' | 'onesided', see :func:`use_symmetric`).
+    ``algorithm`` ('auto' | 'symmetric' | 'onesided', see :func:`use_symmetric`), ``gather`` (with
+    ``group``: 'all' — every rank returns all N rows (default); 'root' — only rank 0 does, the others return
+    the rows of their shard; 'local' — every rank returns the rows of its shard, no gather).
 
     Raises ImportError without a CUDA device / built library, ValueError for
     bad shapes, precision or kernel names, RuntimeError for CUDA failures.
@@ -412,10 +461,10 @@ def compute_nbody_forces_gpu(
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
     mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
-    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np, group, n_src, algorithm)
+    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np, group, n_src, algorithm, gather)
     if return_cupy:
         return acc.as_subclass(DeviceArray)
-    return acc.cpu().numpy()
+    return _to_host(acc)
 
 
 def compute_nbody_potential_gpu(
@@ -433,6 +482,7 @@ def compute_nbody_potential_gpu(
     group=None,
     n_sources=None,
     algorithm=None,
+    gather="all",
 ):
     """Gravitational potential at each particle, ``phi_i = G sum_{j != i} m_j Phi(r_ij)``.
 
@@ -446,10 +496,10 @@ def compute_nbody_potential_gpu(
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
     mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
-    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np, group, n_src, algorithm)
+    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np, group, n_src, algorithm, gather)
     if return_cupy:
         return phi.as_subclass(DeviceArray)
-    return phi.cpu().numpy()
+    return _to_host(phi)
 
 
 def compute_nbody_forces_potential_gpu(
@@ -467,6 +517,7 @@ def compute_nbody_forces_potential_gpu(
     group=None,
     n_sources=None,
     algorithm=None,
+    gather="all",
 ):
     """Accelerations AND potential from one fused sweep (new; the reference needs two
     O(N^2) passes, run.py:611-634).  Returns ``(acc (N,3), phi (N,))``."""
@@ -475,10 +526,10 @@ def compute_nbody_forces_potential_gpu(
     pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
     mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
-    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np, group, n_src, algorithm)
+    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np, group, n_src, algorithm, gather)
     if return_cupy:
         return acc.as_subclass(DeviceArray), phi.as_subclass(DeviceArray)
-    return acc.cpu().numpy(), phi.cpu().numpy()
+    return _to_host(acc), _to_host(phi)
 
 
 def get_gpu_info() -> dict:

@@ -152,6 +152,7 @@ def run_nbody_gpu(
     cuda_graph: bool | None = None,
     exchange: str = "nccl",
     async_io: bool = True,
+    algorithm: str | None = None,
 ) -> np.ndarray:
     """GPU direct-summation N-body run with the KDK leapfrog of the reference.
 
@@ -177,7 +178,10 @@ def run_nbody_gpu(
     ``"nccl"`` all-gathers the packed j-records each step, ``"p2p"`` fuses the exchange into the
     kick+drift kernel, which stores the refreshed records into every rank's buffer over NVLink),
     ``async_io`` (snapshots / periodic restart files are copied to pinned memory on a side stream and
-    written by a worker thread, so file I/O never stalls the step; False = synchronous as in the reference).
+    written by a worker thread, so file I/O never stalls the step; False = synchronous as in the reference),
+    ``algorithm`` (``'auto'``: the pair-symmetric sweep — every unordered pair evaluated once and applied to
+    both particles — from ``nb_sym_min_n()`` particles on, the one-sided sweep below; ``'symmetric'`` /
+    ``'onesided'`` force one; only the one-sided sweep is bitwise reproducible from run to run).
     """
     torch = _lib.require_cuda()   # ImportError when there is no CUDA device / library (reference: "CuPy required")
 
@@ -285,7 +289,7 @@ def run_nbody_gpu(
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     eng = DirectEngine(N, masses, softening, prec, KERNEL_MAP[kernel.lower()], G, EPS2_DEFAULT[prec_key], device,
-                       group=group, overlap=overlap, exchange=exchange)
+                       group=group, overlap=overlap, exchange=exchange, algorithm=algorithm)
     eng.load_state(xv)
 
     want_phi = bool(debug_energy or diagnostics is not None)

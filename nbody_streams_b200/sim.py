@@ -86,7 +86,7 @@ def run_simulation(
     for key in _DF_KWARGS:
         kwargs.pop(key, None)
     # extensions of this package, forwarded to run_nbody_gpu when present
-    ext = {k: kwargs.pop(k) for k in ("device", "group", "overlap", "diagnostics", "diagnostics_every", "cuda_graph", "exchange", "async_io")
+    ext = {k: kwargs.pop(k) for k in ("device", "group", "overlap", "diagnostics", "diagnostics_every", "cuda_graph", "exchange", "async_io", "algorithm")
            if k in kwargs}
 
     if dynamical_friction:

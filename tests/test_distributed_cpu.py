@@ -103,3 +103,103 @@ def test_gather_rows_world1_is_identity():
     x = torch.arange(30.0).reshape(10, 3)
     assert gather_rows(x, L, 0) is x
     assert allgather_shards(torch.zeros(L.n_slots * 4, dtype=torch.uint8), L, 0, L.shard * 4) is None
+
+
+# ---------------------------------------------------------------------------
+# pair-symmetric multi-rank schedule (engine.sym_plan + reduce_scatter_shards)
+# ---------------------------------------------------------------------------
+from nbody_streams_b200.engine import reduce_scatter_shards, sym_plan  # noqa: E402
+
+
+def _plan_tile_pairs(L, rank, tpb):
+    """(i-tile, j-tile, one_sided) work items of one rank, expanded from its plan the way nb_sym.cuh does:
+    block ib sweeps the tiles of its own range from its first tile on (the first `tpb` of them are the
+    one-sided 'diagonal' tiles), ranges A and B, and range C if ibC0 <= ib < ibC1."""
+    p = sym_plan(L, rank, tpb)
+    it0, it1 = p["own"]
+    items = []
+    for ib in range(p["n_ib"]):
+        blk = list(range(it0 + tpb * ib, min(it0 + tpb * (ib + 1), it1)))
+        js = [(t, t < it0 + tpb * (ib + 1)) for t in range(it0 + tpb * ib, it1)]
+        js += [(t, False) for t in range(*p["A"])] + [(t, False) for t in range(*p["B"])]
+        if p["ibC"][0] <= ib < p["ibC"][1]:
+            js += [(t, False) for t in range(*p["C"])]
+        for jt, diag in js:
+            for t in blk:
+                items.append((t, jt, diag))
+    return items
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("n", [100, 256 * 7 + 3, 256 * 64, 256 * 131 + 17])
+@pytest.mark.parametrize("tpb", [2, 4])
+def test_sym_plan_covers_every_tile_pair_exactly_once(world, n, tpb):
+    L = ShardLayout(n, world)
+    R = L.tiles_total
+    ordered = np.zeros((R, R), dtype=int)      # ordered[i, j]: how often particles of tile i receive from tile j
+    for rank in range(world):
+        for it, jt, diag in _plan_tile_pairs(L, rank, tpb):
+            assert 0 <= it < R and 0 <= jt < R, "padding tiles must never be swept"
+            ordered[it, jt] += 1               # i side
+            if not diag:
+                assert it != jt
+                ordered[jt, it] += 1           # j side of a symmetric unit
+    assert (ordered == 1).all()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sym_plan_balances_the_ranks(world):
+    L = ShardLayout(256 * 64 * world, world)
+    work = [sum(1 if d else 2 for _, _, d in _plan_tile_pairs(L, r, 4)) for r in range(world)]
+    assert max(work) <= 1.05 * min(work)
+
+
+def _sym_worker(rank, world, port, out):
+    """Each rank accumulates the partial sums of BOTH sides of its tile pairs (pair sums from the oracle with
+    the source masses restricted to one tile), then the shards are reduce-scattered: the data flow of
+    DirectEngine._compute_sym without the GPU kernel."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, tile = 256 * 5 + 40, 256
+        rng = np.random.default_rng(7)
+        pos = rng.standard_normal((n, 3))
+        mass = rng.uniform(0.5, 1.5, n)
+        L = ShardLayout(n, world)
+
+        def pull(it, jt):   # sum over j in tile jt of m_j K (r_j - r_i) for the rows of tile it
+            m = np.zeros(n)
+            m[jt * tile:(jt + 1) * tile] = mass[jt * tile:(jt + 1) * tile]
+            rows = (it * tile, min((it + 1) * tile, n))
+            return rows, oracle.compute_nbody_forces_cpu(pos, m, H, 1.0, "plummer", rows=rows)
+
+        ws = torch.zeros((L.n_slots, 3), dtype=torch.float64)
+        for it, jt, diag in _plan_tile_pairs(L, rank, 2):
+            rows, a = pull(it, jt)
+            ws[rows[0]:rows[1]] += torch.from_numpy(a)
+            if not diag:
+                rows, a = pull(jt, it)
+                ws[rows[0]:rows[1]] += torch.from_numpy(a)
+        mine = torch.zeros((L.shard, 3), dtype=torch.float64)
+        reduce_scatter_shards(ws, mine, L, rank)
+        full = gather_rows(mine[:L.count(rank)], L, rank)
+        if rank == 0:
+            out.put((full.numpy(), oracle.compute_nbody_forces_cpu(pos, mass, H, 1.0, "plummer")))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_symmetric_partial_sums_reduce_scatter_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sym_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, ref = out.get(timeout=100)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()

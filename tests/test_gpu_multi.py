@@ -24,6 +24,23 @@ def test_sharded_run_matches_single_gpu(tmp_path):
     assert r.returncode == 0 and res.startswith("OK"), f"{res}\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}"
 
 
+@pytest.mark.timeout(900)
+def test_baseline_configs_sharded(tmp_path):
+    """BASELINE configs 3, 4, 5 at full size over all GPUs of the box against oracle rows (mgpu_configs_worker.py)."""
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    worker = Path(__file__).resolve().parent / "mgpu_configs_worker.py"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29537", str(worker), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=850)
+    res = (tmp_path / "result.txt").read_text() if (tmp_path / "result.txt").exists() else ""
+    assert r.returncode == 0 and res.startswith("OK"), f"{res}\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}"
+
+
 def test_device_keyword_selects_a_non_current_gpu(tmp_path):
     """Single process, `device=` pointing at a GPU that is not the current one: same bits as on GPU 0."""
     import numpy as np
