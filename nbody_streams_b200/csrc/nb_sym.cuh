@@ -78,4 +78,68 @@ __host__ __device__ inline int sym_tile(const SymArgs& a, int ib, int jl, bool& 
     return a.rC0 + (jl - a.lenB);
 }
 
+// ---------------------------------------------------------------------------
+// Which units a CTA sweeps.  Units cost different amounts (uniform tiles take the fast path, tiles with
+// per-particle masses / softening or padding the general one, diagonal tiles the masked one), and such tiles
+// come in contiguous stretches of the unit list, so a purely contiguous split would leave whole stretches of
+// slow units to single CTAs.  The list is therefore dealt out in CHUNKS of SYM_CHUNK consecutive units,
+// round-robin over the CTAs (chunk c, c+grid, c+2 grid, ...), for as many complete rounds as there are; the
+// remainder (< grid chunks) is cut into equal contiguous shares like stream-K, so every CTA still gets the
+// same number of units +-1.  Static and arithmetic: no atomics, and the TMA producer can run ahead.
+// A "run" is one chunk or the tail share; SymRuns enumerates the runs of one CTA.
+// ---------------------------------------------------------------------------
+constexpr int SYM_CHUNK = 8;
+
+struct SymRuns {
+    long long rounds;     // complete round-robin rounds of chunks
+    long long tail_b, tail_e;
+    int cta, grid;
+    __device__ SymRuns(const SymArgs& a, int cta_, int grid_) : cta(cta_), grid(grid_) {
+        rounds = (a.total / SYM_CHUNK) / grid;
+        const long long base = rounds * grid * SYM_CHUNK;
+        const long long rem  = a.total - base;
+        tail_b = base + unit_begin(rem, cta, grid);
+        tail_e = base + unit_begin(rem, cta + 1, grid);
+    }
+    __device__ long long n_units() const { return rounds * SYM_CHUNK + (tail_e - tail_b); }
+    __device__ long long n_runs() const { return rounds + (tail_e > tail_b ? 1 : 0); }
+    __device__ void run(long long r, long long& b, long long& e) const {
+        if (r < rounds) {
+            b = (r * grid + cta) * SYM_CHUNK;
+            e = b + SYM_CHUNK;
+        } else {
+            b = tail_b;
+            e = tail_e;
+        }
+    }
+};
+
+// cursor over the units of one CTA in sweep order, decoded to (i-block, local unit)
+template <int TPB>
+struct SymCursor {
+    long long r, u, u_end;   // current run, current unit, end of the run
+    int ib, jl, cnt;
+    __device__ void open(const SymArgs& a, const SymRuns& R, long long run) {
+        r = run;
+        R.run(run, u, u_end);
+        ib  = sym_find_block<TPB>(a, u);
+        jl  = static_cast<int>(u - sym_prefix<TPB>(a, ib));
+        cnt = sym_count<TPB>(a, ib);
+    }
+    // make (ib, jl) valid for the current unit (skips exhausted / empty blocks)
+    __device__ void settle(const SymArgs& a) {
+        while (jl >= cnt) {
+            ++ib;
+            jl  = 0;
+            cnt = sym_count<TPB>(a, ib);
+        }
+    }
+    // advance by n units inside the current run; opens the next run when this one is exhausted
+    __device__ void advance(const SymArgs& a, const SymRuns& R, int n) {
+        u += n;
+        jl += n;
+        if (u >= u_end && r + 1 < R.n_runs()) open(a, R, r + 1);
+    }
+};
+
 }  // namespace nb

@@ -515,7 +515,7 @@ template <int NP>
 struct SymF32Smem {
     static constexpr int kStageBytes = STAGES * TILE_BYTES_F32;
     static constexpr int kBarOff     = (kStageBytes + 63) & ~63;
-    static constexpr int kRunOff     = kBarOff + 64;
+    static constexpr int kRunOff     = kBarOff + 128;   // mbarriers + the TMA producer's unit cursor
     static constexpr int kRunBytes   = 4 * 2 * NP * THREADS * 4;          // float running sums [4][2NP][THREADS]
     static constexpr int kJOff       = kRunOff + kRunBytes;
     static constexpr int kJBytes     = (THREADS / 32) * 4 * TJ * 4;       // j-side slices [warps][4][TJ]
@@ -534,9 +534,8 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x, grid = gridDim.x;
-    const long long u0 = unit_begin(a.total, cta, grid);
-    const long long u1 = unit_begin(a.total, cta + 1, grid);
-    const int n_units  = static_cast<int>(u1 - u0);
+    const SymRuns R(a, cta, grid);            // this CTA's units: round-robin chunks + a stream-K tail share
+    const int n_units = static_cast<int>(R.n_units());
     if (n_units <= 0) return;
     const float eps2 = static_cast<float>(a.eps2);
     const long long i_end = static_cast<long long>(a.it0 + a.nT) * TJ;   // first slot past the i-range
@@ -548,27 +547,24 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
     }
     __syncthreads();
 
-    // unit cursor of the consumer (all threads) and of the TMA producer (thread 0 runs STAGES-1 units ahead)
-    int ib        = sym_find_block<TPB>(a, u0);
-    int jl        = static_cast<int>(u0 - sym_prefix<TPB>(a, ib));
-    int cnt       = sym_count<TPB>(a, ib);
-    int t_ib = ib, t_jl = jl, t_cnt = cnt, issued = 0;
+    // unit cursor of the consumer (all threads, registers) and of the TMA producer (thread 0 only, kept in
+    // shared memory so that it costs no registers in the hot loop); the producer runs STAGES-1 units ahead
+    SymCursor<TPB> cons;
+    cons.open(a, R, 0);
+    SymCursor<TPB>* prod = reinterpret_cast<SymCursor<TPB>*>(smem + L::kBarOff + 64);
+    int issued = 0;
     auto issue_next = [&]() {
-        while (t_jl >= t_cnt) {
-            ++t_ib;
-            t_jl  = 0;
-            t_cnt = sym_count<TPB>(a, t_ib);
-        }
+        prod->settle(a);
         bool dg;
-        const int gt  = sym_tile<TPB>(a, t_ib, t_jl, dg);
+        const int gt  = sym_tile<TPB>(a, prod->ib, prod->jl, dg);
         uint64_t* bar = &full_bar[issued % STAGES];
         mbar_expect_tx(bar, TILE_BYTES_F32);
-        bulk_g2s(smem + (issued % STAGES) * TILE_BYTES_F32, a.packed + static_cast<size_t>(gt) * TILE_BYTES_F32,
-                 TILE_BYTES_F32, bar);
+        bulk_g2s(smem + (issued % STAGES) * TILE_BYTES_F32, a.packed + static_cast<size_t>(gt) * TILE_BYTES_F32, TILE_BYTES_F32, bar);
         ++issued;
-        ++t_jl;
+        prod->advance(a, R, 1);
     };
     if (tid == 0) {
+        prod->open(a, R, 0);
         for (int k = 0; k < STAGES - 1 && k < n_units; ++k) issue_next();
     }
 
@@ -594,13 +590,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
 
     int k = 0;
     while (k < n_units) {
-        if (jl >= cnt) {
-            ++ib;
-            jl  = 0;
-            cnt = sym_count<TPB>(a, ib);
-            continue;
-        }
-        const int seg = min(cnt - jl, n_units - k);
+        cons.settle(a);
+        const int ib  = cons.ib;
+        const int jl0 = cons.jl;
+        const int seg = static_cast<int>(min(static_cast<long long>(cons.cnt - cons.jl), cons.u_end - cons.u));
 
         // ---- this thread's i-pairs (read straight from the packed records) ----
         const int tile0          = a.it0 + TPB * ib;
@@ -659,7 +652,8 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
             }
         };
 
-        for (int t = 0; t < seg; ++t, ++k, ++jl) {
+        for (int t = 0; t < seg; ++t, ++k) {
+            const int jl = jl0 + t;
             __syncthreads();   // everyone is done with tile k-1: its stage may be refilled, its j-slices are complete
             if (tid == 0 && issued < n_units) issue_next();
             if (pend) {
@@ -717,6 +711,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
             }
         }
         if (tiles_in_run) flush_i();
+        cons.advance(a, R, seg);
     }
     __syncthreads();
     if (pend) flush_j();

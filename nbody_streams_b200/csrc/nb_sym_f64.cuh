@@ -230,7 +230,7 @@ template <int NI>
 struct SymF64Smem {
     static constexpr int kStageBytes = SYM_STAGES_F64 * TILE_BYTES_F64;
     static constexpr int kBarOff     = (kStageBytes + 63) & ~63;
-    static constexpr int kRunOff     = kBarOff + 64;
+    static constexpr int kRunOff     = kBarOff + 128;   // mbarriers + the TMA producer's unit cursor
     static constexpr int kRunBytes   = 4 * NI * THREADS * 8;              // double running sums [4][NI][THREADS]
     static constexpr int kJOff       = kRunOff + kRunBytes;
     static constexpr int kJBytes     = (THREADS / 32) * 4 * TJ * 8;       // j-side slices [warps][4][TJ]
@@ -250,9 +250,8 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x, grid = gridDim.x;
-    const long long u0 = unit_begin(a.total, cta, grid);
-    const long long u1 = unit_begin(a.total, cta + 1, grid);
-    const int n_units  = static_cast<int>(u1 - u0);
+    const SymRuns R(a, cta, grid);            // this CTA's units: round-robin chunks + a stream-K tail share
+    const int n_units = static_cast<int>(R.n_units());
     if (n_units <= 0) return;
     const double eps2     = a.eps2;
     const long long i_end = static_cast<long long>(a.it0 + a.nT) * TJ;
@@ -264,26 +263,24 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a)
     }
     __syncthreads();
 
-    int ib  = sym_find_block<TPB>(a, u0);
-    int jl  = static_cast<int>(u0 - sym_prefix<TPB>(a, ib));
-    int cnt = sym_count<TPB>(a, ib);
-    int t_ib = ib, t_jl = jl, t_cnt = cnt, issued = 0;
+    // unit cursor of the consumer (all threads, registers) and of the TMA producer (thread 0 only, kept in
+    // shared memory so that it costs no registers in the hot loop); the producer runs NSTG-1 units ahead
+    SymCursor<TPB> cons;
+    cons.open(a, R, 0);
+    SymCursor<TPB>* prod = reinterpret_cast<SymCursor<TPB>*>(smem + L::kBarOff + 64);
+    int issued = 0;
     auto issue_next = [&]() {
-        while (t_jl >= t_cnt) {
-            ++t_ib;
-            t_jl  = 0;
-            t_cnt = sym_count<TPB>(a, t_ib);
-        }
+        prod->settle(a);
         bool dg;
-        const int gt  = sym_tile<TPB>(a, t_ib, t_jl, dg);
+        const int gt  = sym_tile<TPB>(a, prod->ib, prod->jl, dg);
         uint64_t* bar = &full_bar[issued % NSTG];
         mbar_expect_tx(bar, TILE_BYTES_F64);
-        bulk_g2s(smem + (issued % NSTG) * TILE_BYTES_F64, a.packed + static_cast<size_t>(gt) * TILE_BYTES_F64,
-                 TILE_BYTES_F64, bar);
+        bulk_g2s(smem + (issued % NSTG) * TILE_BYTES_F64, a.packed + static_cast<size_t>(gt) * TILE_BYTES_F64, TILE_BYTES_F64, bar);
         ++issued;
-        ++t_jl;
+        prod->advance(a, R, 1);
     };
     if (tid == 0) {
+        prod->open(a, R, 0);
         for (int k = 0; k < NSTG - 1 && k < n_units; ++k) issue_next();
     }
 
@@ -307,13 +304,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a)
 
     int k = 0;
     while (k < n_units) {
-        if (jl >= cnt) {
-            ++ib;
-            jl  = 0;
-            cnt = sym_count<TPB>(a, ib);
-            continue;
-        }
-        const int seg = min(cnt - jl, n_units - k);
+        cons.settle(a);
+        const int ib  = cons.ib;
+        const int jl0 = cons.jl;
+        const int seg = static_cast<int>(min(static_cast<long long>(cons.cnt - cons.jl), cons.u_end - cons.u));
 
         const int tile0          = a.it0 + TPB * ib;
         const long long ig_block = static_cast<long long>(tile0) * TJ;
@@ -357,7 +351,8 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a)
 #pragma unroll
         for (int e = 0; e < 4 * NI; ++e) run[e * THREADS + tid] = 0.0;
 
-        for (int t = 0; t < seg; ++t, ++k, ++jl) {
+        for (int t = 0; t < seg; ++t, ++k) {
+            const int jl = jl0 + t;
             __syncthreads();   // everyone is done with tile k-1: its stage may be refilled, its j-slices are complete
             if (tid == 0 && issued < n_units) issue_next();
             if (pend) {
@@ -419,6 +414,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a)
                 }
             }
         }
+        cons.advance(a, R, seg);
     }
     __syncthreads();
     if (pend) flush_j();

@@ -54,7 +54,11 @@ def check_config(name, pos, mass, h, precision, kernels, rows, tol, rank, world,
     ok = True
     N = pos.shape[0]
     f64 = precision == "float64"
-    rnd = (lambda a: np.asarray(a, np.float64)) if f64 else (lambda a: np.asarray(a, np.float32).astype(np.float64))
+    def rnd(a):   # what the kernel sees: inputs cast to the kernel dtype (scalars stay scalars)
+        if np.isscalar(a):
+            return float(a) if f64 else float(np.float32(a))
+        return np.asarray(a, np.float64) if f64 else np.asarray(a, np.float32).astype(np.float64)
+
     p64, m64, h64 = rnd(pos), rnd(mass), rnd(h)
     prec, _ = _PRECISION_MAP[precision]
     blocks = row_blocks(N, world, rows)
