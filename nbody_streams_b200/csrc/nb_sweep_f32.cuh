@@ -265,10 +265,13 @@ __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage
 }
 
 // ---------------------------------------------------------------------------
-// Cold paths are kept OUT of the hot loops' register allocation: masked tiles (<= 5 per i-block) and the
-// spline's exact groups run in non-inlined functions that work on a COPY of the thread state (so the
-// state itself never has its address taken and stays in registers in the hot loops).  ptxas schedules
-// the hot loop noticeably worse (measured: -4.6 %) when rare code shares its register allocation.
+// Cold path kept OUT of the hot loops' register allocation: masked tiles (<= 5 per i-block) run in a
+// non-inlined function that works on a COPY of the thread state (so the state itself never has its address
+// taken and stays in registers in the hot loops).  ptxas schedules the hot loop noticeably worse (measured:
+// -4.6 %) when that rare code shares its register allocation.  The spline's exact groups, spline_exact(), are
+// NOT treated that way here: they are inlined into tile_f32_spline behind a branch of the hot loop (the spline
+// kernels carry 28-56 B of spills for it).  The pair-symmetric sweep (nb_sym_f32.cuh), which handles every
+// large-N call, does put its exact step behind a call on a state copy.
 // ---------------------------------------------------------------------------
 template <int KID, int MODE, int NP, int JUF>
 __device__ __noinline__ void tile_f32_masked(const unsigned char* stage, IState<NP>* T, const float eps2,

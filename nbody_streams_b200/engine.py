@@ -559,8 +559,9 @@ class DirectEngine:
                 self._sym_grid(mode)
                 self._sym_buffers()
             else:
-                self._grid(mode)
-                self._workspace(self._grid(mode))      # allocate outside the capture
+                # allocate outside the capture, sized for every mode: a later compute() with another mode must not
+                # reallocate (and thereby free) the buffer whose address is baked into the graph
+                self._workspace(max(self._grid(m) for m in (MODE_FORCE, MODE_POT, MODE_BOTH)))
             graph = torch.cuda.CUDAGraph()
             saved_events, self.sweep_events = self.sweep_events, None
             with torch.cuda.graph(graph, stream=side):

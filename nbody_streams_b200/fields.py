@@ -207,13 +207,13 @@ def use_symmetric(N: int, algorithm: str | None = None) -> bool:
 
 
 def _scratch(device, tag: str, nbytes: int):
-    """Grow-only per-device scratch (packed particle records, stream-K workspace).
-
-    Like the reference's module-level kernel cache (fields.py:396) this is not
-    thread-safe; kernels using it are ordered by the CUDA stream they run on."""
+    """Grow-only scratch (packed particle records, sweep workspace) per (device, CUDA stream): kernels that use
+    a buffer are ordered by the stream they run on, so calls issued on different streams (e.g. from a
+    force_extra hook running on run_nbody_gpu's hook stream) never share one.  Not thread-safe, like the
+    reference's module-level kernel cache (fields.py:396)."""
     import torch
 
-    key = (device.index, tag)
+    key = (device.index, tag, torch.cuda.current_stream(device).cuda_stream)
     buf = _SCRATCH.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = _SCRATCH[key] = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

@@ -16,6 +16,7 @@ follow reference nbody_streams/nbody_io.py so that its ``ParticleReader`` and
 from __future__ import annotations
 
 import math
+import os
 import queue
 import threading
 from pathlib import Path
@@ -115,7 +116,11 @@ def _save_restart(phase_space, time, step, output_dir, snapshot_counter, *, mass
         payload["species_names"] = np.array([n.encode("utf-8") for n in species_names])
     if species_N is not None:
         payload["species_N"] = np.array(species_N, dtype=np.int64)
-    np.savez_compressed(out / "restart.npz", **payload)
+    # write to a temporary file and rename it into place: a crash (or interpreter exit) in the middle of the
+    # write never leaves a truncated restart.npz behind
+    tmp = out / "restart.tmp.npz"
+    np.savez_compressed(tmp, **payload)
+    os.replace(tmp, out / "restart.npz")
 
 
 def _load_restart(output_dir):
@@ -184,8 +189,16 @@ class AsyncStateWriter:
         self.thread = threading.Thread(target=self._worker, name="nbody-io", daemon=True)
         self.thread.start()
 
+    def check(self) -> None:
+        """Raise (once) the exception of a failed write job: called at every submit and once per step, so a full
+        disk or a permission error stops the run at the next step, as the reference's synchronous writes do."""
+        if self.error is not None:
+            err, self.error = self.error, None
+            raise err
+
     def submit(self, kind: str, xv_dev, job) -> None:
         torch = self.torch
+        self.check()
         buf = self.free.get()                       # back-pressure: at most two copies in flight
         cur = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)                # xv_dev was produced on the current stream
@@ -223,11 +236,12 @@ class AsyncStateWriter:
 
     def flush(self) -> None:
         self.jobs.join()
-        if self.error is not None:
-            err, self.error = self.error, None
-            raise err
+        self.check()
 
-    def close(self) -> None:
-        self.flush()
+    def close(self, raise_errors: bool = True) -> None:
+        """Drain the queue, stop the worker, then (optionally) raise a stored write error."""
+        self.jobs.join()
         self.jobs.put(None)
         self.thread.join(timeout=10)
+        if raise_errors:
+            self.check()

@@ -105,19 +105,47 @@ def make_plummer_sphere(N: int, M_total: float = 10_000, a: float = 0.01, seed: 
 # ---------------------------------------------------------------------------
 # external acceleration hooks (reference run.py:197-212, :689-692)
 # ---------------------------------------------------------------------------
-def _external_acc(engine, external_potential, time, full_pos_fn):
-    """(n_local,3) float64 device tensor of the external-potential acceleration."""
+class _PinnedStage:
+    """Two page-locked (n,3) float64 buffers per direction for host potentials: the device->host copy of the
+    positions and the host->device copy of the accelerations are asynchronous copies at PCIe speed, and a
+    buffer is only reused two evaluations later (its previous H2D copy has been waited for by then)."""
+
+    def __init__(self, torch, n):
+        self.torch, self.k = torch, 0
+        self.pos = [torch.empty((max(n, 1), 3), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        self.acc = [torch.empty((max(n, 1), 3), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+
+    def next(self):
+        self.k ^= 1
+        return self.pos[self.k], self.acc[self.k]
+
+
+def _external_acc(engine, external_potential, time, stage=None):
+    """(n_local,3) float64 device tensor of the external-potential acceleration of THIS rank's particles.
+
+    An external potential is a function of position only (reference run.py:197-212 evaluates
+    ``pot.force(pos, t=)`` row by row), so each rank evaluates its own rows: no gather, no redundant CPU work.
+    Runs on torch's current stream (the hook stream of run_nbody_gpu)."""
     torch = engine.torch
+    n = engine.n_local
     if getattr(external_potential, "accepts_device_arrays", False):
         # device potential (PotentialGPU-like): evaluate on the device, no host round trip
-        acc_full = external_potential.force(full_pos_fn().as_subclass(DeviceArray), t=time)
-        acc_full = torch.as_tensor(acc_full, device=engine.device).to(torch.float64)
-    else:
-        # host potential (agama.Potential-like): host round trip, as in the reference
-        pos_cpu = full_pos_fn().cpu().numpy()
-        acc_full = torch.from_numpy(np.asarray(external_potential.force(pos_cpu, t=time), dtype=np.float64)).to(
-            engine.device)
-    return acc_full[engine.layout.rows(engine.rank)].contiguous()
+        acc = external_potential.force(engine.pos.as_subclass(DeviceArray), t=time)
+        if not isinstance(acc, torch.Tensor) and hasattr(acc, "__cuda_array_interface__"):
+            torch.cuda.synchronize(engine.device)    # produced by another library on ITS stream (e.g. CuPy)
+        return torch.as_tensor(acc, device=engine.device).to(torch.float64).contiguous()
+    # host potential (agama.Potential-like): host round trip as in the reference, through pinned buffers
+    cur = torch.cuda.current_stream(engine.device)
+    if stage is None:
+        pos_cpu = engine.pos.cpu().numpy()
+        acc_np = np.asarray(external_potential.force(pos_cpu, t=time), dtype=np.float64)
+        return torch.from_numpy(np.ascontiguousarray(acc_np)).to(engine.device)
+    pos_pin, acc_pin = stage.next()
+    pos_pin[:n].copy_(engine.pos, non_blocking=True)
+    cur.synchronize()                                # only this (hook) stream: the sweep keeps running
+    acc_np = np.asarray(external_potential.force(pos_pin[:n].numpy(), t=time), dtype=np.float64)
+    acc_pin[:n].copy_(torch.from_numpy(np.ascontiguousarray(acc_np).reshape(n, 3)))
+    return acc_pin[:n].to(engine.device, non_blocking=True)
 
 
 def run_nbody_gpu(
@@ -153,6 +181,8 @@ def run_nbody_gpu(
     exchange: str = "nccl",
     async_io: bool = True,
     algorithm: str | None = None,
+    timeline: list | None = None,
+    engine_out: list | None = None,
 ) -> np.ndarray:
     """GPU direct-summation N-body run with the KDK leapfrog of the reference.
 
@@ -181,7 +211,11 @@ def run_nbody_gpu(
     written by a worker thread, so file I/O never stalls the step; False = synchronous as in the reference),
     ``algorithm`` (``'auto'``: the pair-symmetric sweep — every unordered pair evaluated once and applied to
     both particles — from ``nb_sym_min_n()`` particles on, the one-sided sweep below; ``'symmetric'`` /
-    ``'onesided'`` force one; only the one-sided sweep is bitwise reproducible from run to run).
+    ``'onesided'`` force one; only the one-sided sweep is bitwise reproducible from run to run),
+    ``timeline`` (a list that receives, per step with hooks, a dict of timing-enabled CUDA events
+    ``hook_begin`` / ``hook_end`` (hook stream) and ``sweep_end`` (main stream): evidence that the hooks
+    overlap the sweep), ``engine_out`` (a list that receives the DirectEngine of the run — launch counts and
+    device state for benchmarks and tests; without it the engine and its device buffers are released on return).
     """
     torch = _lib.require_cuda()   # ImportError when there is no CUDA device / library (reference: "CuPy required")
 
@@ -217,6 +251,19 @@ def run_nbody_gpu(
     verbose = verbose and is_root
     output_path = Path(output_dir)
 
+    # Root decides (it owns the output directory) and every rank learns the decision, so that a refusal raises
+    # on ALL ranks instead of leaving the others blocked in the first collective; the restart payload is
+    # broadcast too, so ranks with a non-shared output_dir resume from the same step.
+    def _root_says(value):
+        if world == 1:
+            return value
+        import torch.distributed as dist
+
+        box = [value]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return box[0]
+
+    refusal = None
     if save_snapshots and not continue_run and is_root:
         existing = sorted(output_path.glob("snapshot*.h5"))
         if existing:
@@ -226,18 +273,19 @@ def run_nbody_gpu(
                 if verbose:
                     print(f"Removed {len(existing)} existing snapshot file(s) in '{output_dir}'.")
             else:
-                raise FileExistsError(
-                    f"Output directory '{output_dir}' already contains snapshot files: "
-                    f"{[f.name for f in existing]}. "
-                    "Pass overwrite=True to delete them, or continue_run=True to resume."
-                )
+                refusal = (f"Output directory '{output_dir}' already contains snapshot files: "
+                           f"{[f.name for f in existing]}. "
+                           "Pass overwrite=True to delete them, or continue_run=True to resume.")
+    refusal = _root_says(refusal)
+    if refusal is not None:
+        raise FileExistsError(refusal)
 
     start_step = 0
     time = time_start
     snapshot_counter = None
     xv = phase_space
     if continue_run:
-        restart_data = _load_restart(output_path)
+        restart_data = _root_says(_load_restart(output_path) if is_root else None)
         if restart_data is not None:
             xv, time, start_step, saved_snap_counter = restart_data[:4]
             snapshot_counter = int(saved_snap_counter)
@@ -303,43 +351,62 @@ def run_nbody_gpu(
     def full_vel():
         return gather_rows(eng.vel, eng.layout, eng.rank, eng.group)
 
+    host_potential = external_potential is not None and not getattr(external_potential, "accepts_device_arrays", False)
+    stage = _PinnedStage(torch, eng.n_local) if host_potential else None
+
     def extra_acc(step, t):
-        """Sum of external-potential (cached) and force_extra accelerations for this rank's rows."""
+        """External-potential acceleration (cached for external_update_interval steps) of this rank's rows."""
         nonlocal cached_ext
-        total = None
-        if external_potential is not None:
-            if step % external_update_interval == 0 or cached_ext is None:
-                cached_ext = _external_acc(eng, external_potential, t, full_pos)
-            total = cached_ext
-        return total
+        if external_potential is None:
+            return None
+        if step % external_update_interval == 0 or cached_ext is None:
+            cached_ext = _external_acc(eng, external_potential, t, stage)
+        return cached_ext
 
     def add_force_extra(total, t):
+        # force_extra(pos, vel, masses, t) sees ALL particles (reference run.py:689-692): rows are gathered
         fe = force_extra(full_pos().as_subclass(DeviceArray), full_vel().as_subclass(DeviceArray), masses, t)
-        if not isinstance(fe, torch.Tensor) and not hasattr(fe, "__cuda_array_interface__"):
-            fe = np.asarray(fe)               # host result: one H2D copy, as cp.asarray in the reference
+        if not isinstance(fe, torch.Tensor):
+            if hasattr(fe, "__cuda_array_interface__"):
+                torch.cuda.synchronize(eng.device)   # produced by another library on ITS stream (e.g. CuPy)
+            else:
+                fe = np.asarray(fe)           # host result: one H2D copy, as cp.asarray in the reference
         fe = torch.as_tensor(fe, device=eng.device).to(torch.float64)[eng.layout.rows(eng.rank)]
         return fe.contiguous() if total is None else (total + fe).contiguous()
 
-    # Hooks run on their own stream (single rank): positions are final once the drift kernel has run, so the
-    # device->host copy for a host potential, the CPU evaluation (agama-like: 10-20 ms in the reference's own
-    # docs) and the host->device copy of the result all overlap the O(N^2) sweep queued on the main stream.
-    # The reference serialises them (run.py:197-212, :689-692).
+    # Hooks run on their own stream: positions are final once the drift kernel has run, so the device->host copy
+    # for a host potential, the CPU evaluation (agama-like: 10-20 ms in the reference's own docs) and the
+    # host->device copy of the result all overlap the O(N^2) sweep queued on the main stream.  The reference
+    # serialises them (run.py:197-212, :689-692).  Hook code must launch its device work on torch's CURRENT stream
+    # (torch does by default; results of other libraries are synchronised device-wide before use).
+    # With several ranks the external potential still runs on the side stream (local rows, no collective);
+    # force_extra needs the gathered arrays and therefore stays on the main stream, after the sweep is queued.
     hook_stream = torch.cuda.Stream(eng.device) if hooks else None
     ev_drift = torch.cuda.Event() if hooks else None
 
     def eval_hooks(step, t, with_force_extra):
         cur = torch.cuda.current_stream(eng.device)
-        if world > 1:
-            total = extra_acc(step, t)
-            return add_force_extra(total, t) if with_force_extra else total
+        rec = None
+        if timeline is not None:
+            rec = {"step": step, "hook_begin": torch.cuda.Event(enable_timing=True),
+                   "hook_end": torch.cuda.Event(enable_timing=True), "sweep_end": torch.cuda.Event(enable_timing=True)}
+            rec["sweep_end"].record(cur)                     # the sweep + finish are already queued on `cur`
         hook_stream.wait_event(ev_drift)
         with torch.cuda.stream(hook_stream):
+            if rec is not None:
+                rec["hook_begin"].record(hook_stream)
             total = extra_acc(step, t)
-            if with_force_extra:
+            if with_force_extra and world == 1:
                 total = add_force_extra(total, t)
+            if rec is not None:
+                rec["hook_end"].record(hook_stream)
         cur.wait_stream(hook_stream)
         if total is not None:
             total.record_stream(cur)
+        if with_force_extra and world > 1:
+            total = add_force_extra(total, t)
+        if rec is not None:
+            timeline.append(rec)
         return total
 
     if verbose:
@@ -405,69 +472,96 @@ def run_nbody_gpu(
     graph_step = eng.capture_step(mode, dt) if (cuda_graph and world == 1 and not hooks and remaining_steps > 0
                                                  and eng.n_local > 0) else None
 
-    for step_i in range(1, remaining_steps + 1):
-        current_step = start_step + step_i
+    # Error handling.  A failed file write of the async worker is noticed at the end of the step in which it
+    # failed: the loop stops there, the (consistent) state of that step is written to restart.npz synchronously,
+    # and the I/O error is raised — the reference's synchronous writes fail at the same point.  If the loop itself
+    # raises (a hook, Ctrl-C) the state may be in the middle of a step, so no new restart is written; the writer
+    # is drained and stopped (restart.npz is replaced atomically, so the last periodic one is intact) and the
+    # error propagates.
+    loop_error = io_error = None
+    steps_done = start_step
+    try:
+        for step_i in range(1, remaining_steps + 1):
+            current_step = start_step + step_i
 
-        if graph_step is not None:
-            graph_step()                     # the same four launches, replayed as one CUDA graph
-            time += dt
-        else:
-            eng.kick_drift(dt, acc_ext)          # half kick + drift (+ repack own shard), fused
-            if hooks:
-                ev_drift.record(torch.cuda.current_stream(eng.device))
-            time += dt
-            eng.compute(mode)                    # all-gather (world>1) + sweep + finish (asynchronous)
-            if hooks:                            # evaluated while the sweep runs
-                acc_ext = eval_hooks(current_step, time, force_extra is not None)
-            eng.kick(dt, acc_ext)                # half kick
+            if graph_step is not None:
+                graph_step()                     # the same four launches, replayed as one CUDA graph
+                time += dt
+            else:
+                eng.kick_drift(dt, acc_ext)          # half kick + drift (+ repack own shard), fused
+                if hooks:
+                    ev_drift.record(torch.cuda.current_stream(eng.device))
+                time += dt
+                eng.compute(mode)                    # all-gather (world>1) + sweep + finish (asynchronous)
+                if hooks:                            # evaluated while the sweep runs
+                    acc_ext = eval_hooks(current_step, time, force_extra is not None)
+                eng.kick(dt, acc_ext)                # half kick
 
-        while snapshot_counter < len(snapshot_steps) and current_step >= snapshot_steps[snapshot_counter]:
-            if save_snapshots:
-                write_state("snapshot", snapshot_counter, time, current_step)
+            while snapshot_counter < len(snapshot_steps) and current_step >= snapshot_steps[snapshot_counter]:
+                if save_snapshots:
+                    write_state("snapshot", snapshot_counter, time, current_step)
+                    if verbose:
+                        print(f"Saved snapshot id={snapshot_counter:03d} at step {current_step}, time {time:.6e}...",
+                              flush=True)
+                snapshot_counter += 1
+
+            if diagnostics is not None and diagnostics_every and (step_i % diagnostics_every == 0 or
+                                                                  step_i == remaining_steps):
+                KE, PE, e = energies()
+                diagnostics.append((current_step, time, KE, PE, float(e[2]), float(e[3]), float(e[4])))
+
+            if (verbose or debug_energy) and step_i % _report_every == 0:
+                line = None
                 if verbose:
-                    print(f"Saved snapshot id={snapshot_counter:03d} at step {current_step}, time {time:.6e}...",
-                          flush=True)
+                    elapsed = pytime.perf_counter() - t_start
+                    rate = step_i / elapsed if elapsed > 0 else 0
+                    eta = (remaining_steps - step_i) / rate if rate > 0 else 0
+                    line = (f"  Step {current_step:>6}/{total_steps} | t={time:.4e} | "
+                            f"Snapshots: {snapshot_counter}/{len(snapshot_steps)} | {rate:.1f} steps/s | "
+                            f"avg {elapsed / step_i * 1000:.1f}ms/step | ETA {eta:.0f}s")
+                if debug_energy and E_ref != 0.0:
+                    KE, PE, _ = energies()          # collective: every rank takes part
+                    dE = (KE + PE - E_ref) / abs(E_ref)
+                    Q = KE / abs(PE) if PE != 0.0 else float("nan")
+                    if line is not None:
+                        line += f" | Q={Q:.3f}  dE/E={dE:+.2e}"
+                if line is not None:
+                    print(line, flush=True)
+
+            if current_step > 0 and (current_step % restart_interval) == 0:
+                write_state("restart", snapshot_counter, time, current_step)
+            steps_done = current_step
+            if writer is not None:
+                try:
+                    writer.check()
+                except BaseException as e:  # noqa: BLE001 - raised after the restart file is safe
+                    io_error = e
+                    break
+
+        if io_error is None and snapshot_counter < len(snapshot_steps) and snapshot_steps[-1] == total_steps:
+            if save_snapshots:
+                if verbose:
+                    print(f"<=Saving final snapshot snap.{snapshot_counter:03d} at step {total_steps}, "
+                          f"time {time:.6e}=>")
+                write_state("snapshot", snapshot_counter, time, total_steps)
             snapshot_counter += 1
 
-        if diagnostics is not None and diagnostics_every and (step_i % diagnostics_every == 0 or
-                                                              step_i == remaining_steps):
-            KE, PE, e = energies()
-            diagnostics.append((current_step, time, KE, PE, float(e[2]), float(e[3]), float(e[4])))
-
-        if (verbose or debug_energy) and step_i % _report_every == 0:
-            line = None
-            if verbose:
-                elapsed = pytime.perf_counter() - t_start
-                rate = step_i / elapsed if elapsed > 0 else 0
-                eta = (remaining_steps - step_i) / rate if rate > 0 else 0
-                line = (f"  Step {current_step:>6}/{total_steps} | t={time:.4e} | "
-                        f"Snapshots: {snapshot_counter}/{len(snapshot_steps)} | {rate:.1f} steps/s | "
-                        f"avg {elapsed / step_i * 1000:.1f}ms/step | ETA {eta:.0f}s")
-            if debug_energy and E_ref != 0.0:
-                KE, PE, _ = energies()          # collective: every rank takes part
-                dE = (KE + PE - E_ref) / abs(E_ref)
-                Q = KE / abs(PE) if PE != 0.0 else float("nan")
-                if line is not None:
-                    line += f" | Q={Q:.3f}  dE/E={dE:+.2e}"
-            if line is not None:
-                print(line, flush=True)
-
-        if current_step > 0 and (current_step % restart_interval) == 0:
-            write_state("restart", snapshot_counter, time, current_step)
-
-    if snapshot_counter < len(snapshot_steps) and snapshot_steps[-1] == total_steps:
-        if save_snapshots:
-            if verbose:
-                print(f"<=Saving final snapshot snap.{snapshot_counter:03d} at step {total_steps}, "
-                      f"time {time:.6e}=>")
-            write_state("snapshot", snapshot_counter, time, total_steps)
-        snapshot_counter += 1
-
+    except BaseException as e:  # noqa: BLE001 - re-raised below, once the writer thread is stopped
+        loop_error = e
+    if loop_error is not None:
+        if writer is not None:
+            writer.close(raise_errors=False)
+        raise loop_error
     xv_final_cpu = host_state()
     if writer is not None:
-        writer.close()                      # everything queued is on disk before the final restart is written
+        try:
+            writer.close()                      # everything queued is on disk before the final restart is written
+        except BaseException as e:  # noqa: BLE001
+            io_error = io_error or e
     if is_root:
-        _save_restart(xv_final_cpu, time, total_steps, output_path, snapshot_counter, **_restart_kwargs)
+        _save_restart(xv_final_cpu, time, steps_done, output_path, snapshot_counter, **_restart_kwargs)
+    if io_error is not None:
+        raise io_error
 
     if verbose:
         total_time = pytime.perf_counter() - t_start
@@ -482,7 +576,8 @@ def run_nbody_gpu(
         print(f"Snapshots saved: {snapshot_counter}")
         print("=" * 80)
 
-    run_nbody_gpu.last_engine = eng   # for benchmarks / tests: launch counts, device state
+    if engine_out is not None:
+        engine_out.append(eng)
     return xv_final_cpu
 
 

@@ -60,9 +60,11 @@ def main():
 
     # exchange fused into the drift kernel: NVLink peer stores / NVSwitch multicast through torch symmetric memory
     if "--p2p" in sys.argv:
-        p2p = nb.run_nbody_gpu(xv, mass, 0.0, steps * dt, dt, h, output_dir=str(out / "p2p"), exchange="p2p", **kw)
+        eng_box = []
+        p2p = nb.run_nbody_gpu(xv, mass, 0.0, steps * dt, dt, h, output_dir=str(out / "p2p"), exchange="p2p",
+                               engine_out=eng_box, **kw)
         e_p2p = np.abs(p2p - ref).max() / np.abs(ref).max()
-        eng = nb.run_nbody_gpu.last_engine
+        eng = eng_box[-1]
         msgs.append(f"run float64 exchange=p2p vs 1 GPU: {e_p2p:.2e} (bitwise equal to NCCL overlap run: "
                     f"{np.array_equal(p2p, ovl)}; multicast {'yes' if eng._mc_ptr else 'no'})")
         ok &= bool(e_p2p < 1e-12) and bool(np.array_equal(p2p, ovl))
@@ -93,6 +95,44 @@ def main():
     ok &= bool(np.array_equal(flat["/snapshots/snap.000"], xv)) and bool(np.array_equal(flat["/snapshots/snap.002"], sn))
     ok &= bool(np.array_equal(sn, ovl)) and "/snapshots/snap.001" in flat
     msgs.append(f"snapshots from a sharded run: 3 written, last equals the returned state {np.array_equal(flat['/snapshots/snap.002'], sn)}")
+
+    # hooks on several ranks: a host potential and a device potential are evaluated on each rank's OWN rows (no
+    # gather, side stream); force_extra still sees the gathered arrays.  Same trajectory as on one GPU.
+    class Harmonic:
+        def force(self, pos, t=0.0):
+            assert len(pos) < N                      # local rows only
+            return -0.5 * np.asarray(pos)
+
+    class HarmonicGPU:
+        accepts_device_arrays = True
+
+        def force(self, pos, t=0.0):
+            return -0.5 * pos
+
+    seen = []
+
+    def drag(pos, vel, masses, t):
+        seen.append(pos.shape[0])
+        return -0.01 * vel.get()
+
+    groups = [dist.new_group(ranks=[r]) for r in range(world)]
+
+    class HarmonicAny(Harmonic):
+        def force(self, pos, t=0.0):
+            return -0.5 * np.asarray(pos)
+
+    tl = []
+    hk = dict(kw, external_potential=Harmonic(), force_extra=drag)
+    h_w = nb.run_nbody_gpu(xv, mass, 0.0, steps * dt, dt, h, output_dir=str(out / "hook_w"), timeline=tl, **hk)
+    h_g = nb.run_nbody_gpu(xv, mass, 0.0, steps * dt, dt, h, output_dir=str(out / "hook_g"),
+                           **dict(kw, external_potential=HarmonicGPU(), force_extra=drag))
+    h_1 = nb.run_nbody_gpu(xv, mass, 0.0, steps * dt, dt, h, output_dir=str(out / f"hook_1_{rank}"), group=groups[rank],
+                           **dict(kw, external_potential=HarmonicAny(), force_extra=drag))
+    e_h = np.abs(h_w - h_1).max() / np.abs(h_1).max()
+    e_g = np.abs(h_g - h_1).max() / np.abs(h_1).max()
+    msgs.append(f"hooks on {world} ranks vs 1 GPU: host potential {e_h:.2e}, device potential {e_g:.2e}; "
+                f"force_extra saw {set(seen)} rows; timeline records {len(tl)}")
+    ok &= bool(e_h < 1e-12) and bool(e_g < 1e-12) and set(seen) == {N} and len(tl) == steps + 1
 
     # iterative unbinding with the target rows sharded over the ranks: masks identical on every rank and
     # equal to the single-GPU result
