@@ -265,7 +265,8 @@ int nb_sweep(int prec, int kernel_id, int mode, const void* packed, long n_j, in
     a.n_ib = static_cast<int>((n_i + IB - 1) / IB);
     a.i_begin = i_begin;
     a.n_i = n_i;
-    a.total = static_cast<long long>(a.n_ib) * a.n_jt;
+    a.split_log2 = pick_split_log2(a.n_ib, a.n_jt, grid);
+    a.total = static_cast<long long>(a.n_ib) * (static_cast<long long>(a.n_jt) << a.split_log2);
     a.eps2 = eps2;
     unsigned char* base = static_cast<unsigned char*>(workspace) + L.slot_bytes * static_cast<size_t>(slot);
     a.full = base;
@@ -283,8 +284,13 @@ int nb_finish(int prec, int kernel_id, int mode, long n_i, int grid, int n_sweep
     if (!(mode & NB_MODE_FORCE)) acc = nullptr;
     if (!(mode & NB_MODE_POT)) phi = nullptr;
     const SlotLayout L = slot_layout(prec, n_i, grid);
-    return nb_launch_finish(prec, n_i, grid, block_i_for(prec, kernel_id, mode), n_sweeps, n_jt, workspace, L.slot_bytes,
-                            L.part_off, G, acc, phi, static_cast<cudaStream_t>(stream));
+    // units per i-block of every slot, with the same sub-tile split nb_sweep chose for it
+    const int IB = block_i_for(prec, kernel_id, mode);
+    const long long n_ib = (n_i + IB - 1) / IB;
+    int upb[4] = {0, 0, 0, 0};
+    for (int s = 0; s < n_sweeps; ++s) upb[s] = n_jt[s] > 0 ? n_jt[s] << pick_split_log2(n_ib, n_jt[s], grid) : 0;
+    return nb_launch_finish(prec, n_i, grid, IB, n_sweeps, upb, workspace, L.slot_bytes, L.part_off, G, acc, phi,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int nb_direct(int prec, int kernel_id, int mode, const void* pos, int pos_dt, const void* mass, int mass_dt,

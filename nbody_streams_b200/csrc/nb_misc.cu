@@ -95,31 +95,52 @@ struct FinishArgs {
     double G;
 };
 
-template <typename PT /*float4|double4*/, typename OT /*float|double*/>
+// CTA that owns unit u of `total` units split over `grid` CTAs: the largest c with unit_begin(c) <= u.
+// 32-bit arithmetic whenever the products fit (always in the small-N regime this kernel matters for).
+__device__ __forceinline__ int cta_of_unit(long long u, long long total, int grid, bool small) {
+    if (small) {
+        const unsigned t = static_cast<unsigned>(total);
+        return static_cast<int>((static_cast<unsigned>(u + 1) * static_cast<unsigned>(grid) + t - 1u) / t) - 1;
+    }
+    return static_cast<int>(((u + 1) * grid + total - 1) / total) - 1;
+}
+__device__ __forceinline__ long long unit_begin_fast(long long total, int c, int grid, bool small) {
+    if (small) return static_cast<long long>((static_cast<unsigned>(total) * static_cast<unsigned>(c)) / static_cast<unsigned>(grid));
+    return unit_begin(total, c, grid);
+}
+
+// TPI threads share one i-particle: thread r takes the pieces k = r, r + TPI, ... (ascending) and the TPI
+// partial sums are combined in a fixed order, so the result does not depend on scheduling.  At small N an
+// i-block is cut into dozens of pieces (one per CTA that touched it); walking them with one thread per i was
+// 10-35 us of pure latency.
+template <typename PT /*float4|double4*/, typename OT /*float|double*/, int TPI>
 __global__ void finish_kernel(const FinishArgs a, OT* __restrict__ acc, OT* __restrict__ phi) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= a.n_i) return;
-    const int ib = static_cast<int>(i / a.IB);
-    const int li = static_cast<int>(i - static_cast<long long>(ib) * a.IB);
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long i = t / TPI;
+    const int r = static_cast<int>(t - i * TPI);
+    const bool live = i < a.n_i;
+    const long long ii = live ? i : a.n_i - 1;            // idle lanes shadow a valid i (shuffles need every lane)
+    const int ib = static_cast<int>(ii / a.IB);
+    const int li = static_cast<int>(ii - static_cast<long long>(ib) * a.IB);
     double sx = 0.0, sy = 0.0, sz = 0.0, sp = 0.0;
     for (int s = 0; s < a.n_sweeps; ++s) {
-        const int n_jt = a.n_jt[s];
+        const int n_jt = a.n_jt[s];                       // work units per i-block of this slot
         if (n_jt <= 0) continue;
         const unsigned char* slot = a.ws + static_cast<size_t>(s) * a.slot_bytes;
         const PT* full = reinterpret_cast<const PT*>(slot);
         const PT* part = reinterpret_cast<const PT*>(slot + a.part_off);
         const long long total = static_cast<long long>(a.n_ib) * n_jt;
+        const bool small = (total + 1) * a.grid < (1LL << 31);
         const long long ub = static_cast<long long>(ib) * n_jt, ue = ub + n_jt;
-        // Walk the pieces of [ub, ue) in ascending unit (= ascending CTA) order.  The CTA holding unit u is the
-        // largest c with unit_begin(c) <= u; computing it directly skips the CTAs with an empty range (most of
-        // the grid when there are fewer units than CTAs, i.e. N of a few thousand).
-        const bool dense = total >= a.grid;          // every CTA owns at least one unit: the next piece is CTA c+1
-        int c = static_cast<int>(((ub + 1) * a.grid + total - 1) / total) - 1;
-        if (c >= a.grid) c = a.grid - 1;
-        long long cb = unit_begin(total, c, a.grid);
-        long long u = ub;
-        while (u < ue) {
-            const long long ce = unit_begin(total, c + 1, a.grid);
+        // pieces of [ub, ue) in ascending unit (= ascending CTA) order.  dense: every CTA owns at least one unit,
+        // so piece k belongs to CTA c0 + k; otherwise every unit is its own piece (most CTAs are empty)
+        const bool dense = total >= a.grid;
+        const int c0 = cta_of_unit(ub, total, a.grid, small);
+        const int n_pieces = dense ? cta_of_unit(ue - 1, total, a.grid, small) - c0 + 1 : n_jt;
+        for (int k = r; k < n_pieces; k += TPI) {
+            const int c = dense ? c0 + k : cta_of_unit(ub + k, total, a.grid, small);
+            const long long cb = unit_begin_fast(total, c, a.grid, small);
+            const long long ce = unit_begin_fast(total, c + 1, a.grid, small);
             const long long sb = cb > ub ? cb : ub, se = ce < ue ? ce : ue;
             PT v;
             if (sb == ub && se == ue) v = full[static_cast<size_t>(ib) * a.IB + li];
@@ -128,17 +149,18 @@ __global__ void finish_kernel(const FinishArgs a, OT* __restrict__ acc, OT* __re
             sy += static_cast<double>(v.y);
             sz += static_cast<double>(v.z);
             sp += static_cast<double>(v.w);
-            u = se;
-            if (u >= ue) break;
-            if (dense) {
-                ++c;
-                cb = ce;
-            } else {
-                c = static_cast<int>(((u + 1) * a.grid + total - 1) / total) - 1;
-                cb = unit_begin(total, c, a.grid);
-            }
         }
     }
+    if (TPI > 1) {
+#pragma unroll
+        for (int off = 1; off < TPI; off <<= 1) {          // fixed combination order: (0+1) + (2+3)
+            sx += __shfl_xor_sync(0xffffffffu, sx, off);
+            sy += __shfl_xor_sync(0xffffffffu, sy, off);
+            sz += __shfl_xor_sync(0xffffffffu, sz, off);
+            sp += __shfl_xor_sync(0xffffffffu, sp, off);
+        }
+    }
+    if (!live || r != 0) return;
     if (acc) {
         acc[3 * i + 0] = static_cast<OT>(a.G * sx);
         acc[3 * i + 1] = static_cast<OT>(a.G * sy);
@@ -362,15 +384,20 @@ int nb_launch_finish(int prec, long long n_i, int grid, int IB, int n_sweeps, co
     a.n_ib = static_cast<int>((n_i + IB - 1) / IB);
     a.n_i = n_i;
     a.G = G;
-    const int threads = n_i >= 148 * 256 ? 256 : 64;      // small N: spread the rows over more SMs
-    const unsigned blocks = static_cast<unsigned>((n_i + threads - 1) / threads);
-    if (prec == NB_PREC_F32)
-        finish_kernel<float4, float><<<blocks, threads, 0, st>>>(a, static_cast<float*>(acc), static_cast<float*>(phi));
-    else if (prec == NB_PREC_F64)
-        finish_kernel<double4, double><<<blocks, threads, 0, st>>>(a, static_cast<double*>(acc),
-                                                                   static_cast<double*>(phi));
-    else
-        finish_kernel<double4, float><<<blocks, threads, 0, st>>>(a, static_cast<float*>(acc), static_cast<float*>(phi));
+    // small N: 4 threads per i and small blocks (latency-bound piece walk); large N: one thread per i
+    const bool small = n_i < 148 * 256;
+    const int threads = small ? 64 : 256;
+    const int tpi = small ? 4 : 1;
+    const unsigned blocks = static_cast<unsigned>((n_i * tpi + threads - 1) / threads);
+#define NB_FINISH(PT, OT)                                                                                         \
+    do {                                                                                                          \
+        if (small) finish_kernel<PT, OT, 4><<<blocks, threads, 0, st>>>(a, static_cast<OT*>(acc), static_cast<OT*>(phi)); \
+        else finish_kernel<PT, OT, 1><<<blocks, threads, 0, st>>>(a, static_cast<OT*>(acc), static_cast<OT*>(phi));       \
+    } while (0)
+    if (prec == NB_PREC_F32) NB_FINISH(float4, float);
+    else if (prec == NB_PREC_F64) NB_FINISH(double4, double);
+    else NB_FINISH(double4, float);
+#undef NB_FINISH
     NB_CUDA_OK(cudaGetLastError());
     return 0;
 }

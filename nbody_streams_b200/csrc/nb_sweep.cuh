@@ -19,9 +19,11 @@ struct SweepArgs {
     long long n_pad;              // padded particle count (whole tiles)
     int jtA0, lenA, jtB0, lenB;   // j-tile ranges; local tile jl -> jl<lenA ? jtA0+jl : jtB0+jl-lenA
     int n_jt;                     // lenA + lenB
+    int split_log2;               // a tile is swept in 2^split_log2 parts, one work unit each (small N: more units
+                                  // than CTAs); units per i-block upb = n_jt << split_log2
     int n_ib;                     // number of i-blocks
     long long i_begin, n_i;       // global index of first i, count
-    long long total;              // n_ib * n_jt work units
+    long long total;              // n_ib * upb work units
     double eps2;
     unsigned char* full;          // [n_ib * IB] partial elements
     unsigned char* part;          // [grid * 2 * IB] partial elements
@@ -31,6 +33,16 @@ struct SweepArgs {
 // float for NB_PREC_F32, double otherwise.
 __host__ __device__ inline size_t partial_elem_bytes(int prec) { return prec == NB_PREC_F32 ? 16 : 32; }
 __host__ __device__ inline int block_i(int prec) { return prec == NB_PREC_F64 ? IB_F64 : IB_F32; }
+
+// Sub-tile work units for small problems: with fewer than two units per CTA the persistent grid is mostly idle
+// (N = 10k in float32: 800 units for 740 CTAs, makespan 2 against a mean of 1.08), so tiles are cut into 2 or 4
+// parts (N = 10k: 3200 quarter-tile units, makespan 5 against a mean of 4.3).  nb_sweep and nb_finish derive the same split from (n_ib, n_jt, grid).
+__host__ __device__ inline int pick_split_log2(long long n_ib, long long n_jt, int grid) {
+    const long long units = n_ib * n_jt;        // aim at >= 4 units per CTA: the tail is then <= 1/4 of the sweep
+    if (units >= 4LL * grid) return 0;
+    if (2 * units >= 4LL * grid) return 1;
+    return 2;
+}
 
 __device__ __forceinline__ int local_to_global_tile(const SweepArgs& a, int jl) {
     return jl < a.lenA ? a.jtA0 + jl : a.jtB0 + (jl - a.lenA);

@@ -155,7 +155,7 @@ struct IState {
 template <int KID, int MODE, bool MASK, bool UM, bool UC, int NP, int JUF>
 __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage, IState<NP>& S, const float eps2,
                                          const float c_tile, const long long jg0, const long long ig0,
-                                         const long long n_j) {
+                                         const long long n_j, const int jb = 0, const int je = TJ) {
     const float* __restrict__ sX = reinterpret_cast<const float*>(stage) + COMP_X * TJ;
     const float* __restrict__ sY = reinterpret_cast<const float*>(stage) + COMP_Y * TJ;
     const float* __restrict__ sZ = reinterpret_cast<const float*>(stage) + COMP_Z * TJ;
@@ -179,7 +179,7 @@ __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage
     }
 
 #pragma unroll 1
-    for (int j0 = 0; j0 < TJ; j0 += JU) {
+    for (int j0 = jb; j0 < je; j0 += JU) {   // [jb, je): the whole tile, or one part of it (sub-tile work units)
         float xs[8], ys[8], zs[8], ms[8], cs[8];
         if (JU >= 4) {   // broadcast LDS.128: four j-particles per load
 #pragma unroll
@@ -275,8 +275,9 @@ __device__ __forceinline__ void tile_f32(const unsigned char* __restrict__ stage
 // ---------------------------------------------------------------------------
 template <int KID, int MODE, int NP, int JUF>
 __device__ __noinline__ void tile_f32_masked(const unsigned char* stage, IState<NP>* T, const float eps2,
-                                             const long long jg0, const long long ig0, const long long n_j) {
-    tile_f32<KID, MODE, true, false, false, NP, JUF>(stage, *T, eps2, 0.f, jg0, ig0, n_j);
+                                             const long long jg0, const long long ig0, const long long n_j,
+                                             const int jb = 0, const int je = TJ) {
+    tile_f32<KID, MODE, true, false, false, NP, JUF>(stage, *T, eps2, 0.f, jg0, ig0, n_j, jb, je);
 }
 
 // ---------------------------------------------------------------------------
@@ -316,7 +317,8 @@ __device__ __forceinline__ void spline_exact(const float xj, const float yj, con
 
 template <int MODE, bool UM, int NP>
 __device__ __forceinline__ void tile_f32_spline(const unsigned char* __restrict__ stage, IState<NP>& S,
-                                                const float eps2, const float c_max_tile) {
+                                                const float eps2, const float c_max_tile, const int jb = 0,
+                                                const int je = TJ) {
     const float* __restrict__ sX = reinterpret_cast<const float*>(stage) + COMP_X * TJ;
     const float* __restrict__ sY = reinterpret_cast<const float*>(stage) + COMP_Y * TJ;
     const float* __restrict__ sZ = reinterpret_cast<const float*>(stage) + COMP_Z * TJ;
@@ -328,7 +330,7 @@ __device__ __forceinline__ void tile_f32_spline(const unsigned char* __restrict_
     const f2 ceps = splat(eps2);
 
 #pragma unroll 1
-    for (int j0 = 0; j0 < TJ; j0 += 4) {
+    for (int j0 = jb; j0 < je; j0 += 4) {
         const float4 x4 = *reinterpret_cast<const float4*>(sX + j0);
         const float4 y4 = *reinterpret_cast<const float4*>(sY + j0);
         const float4 z4 = *reinterpret_cast<const float4*>(sZ + j0);
@@ -440,9 +442,12 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
     }
     __syncthreads();
 
+    const int sl  = a.split_log2;
+    const int upb = a.n_jt << sl;               // work units per i-block
+    const int plen = TJ >> sl;                  // j-particles per unit
     auto issue = [&](int k) {   // elected thread: TMA bulk load of unit k's j-tile
         const long long u = u0 + k;
-        const int jl      = static_cast<int>(u % a.n_jt);
+        const int jl      = static_cast<int>(u % upb) >> sl;
         const int gt      = local_to_global_tile(a, jl);
         uint64_t* bar     = &full_bar[k % STAGES];
         mbar_expect_tx(bar, TILE_BYTES_F32);
@@ -456,10 +461,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
     long long u = u0;
     int k = 0;
     while (u < u1) {
-        const int ib  = static_cast<int>(u / a.n_jt);
-        const int jl0 = static_cast<int>(u - static_cast<long long>(ib) * a.n_jt);
+        const int ib  = static_cast<int>(u / upb);
+        const int jl0 = static_cast<int>(u - static_cast<long long>(ib) * upb);   // first unit of the segment
         const long long rem = u1 - u;
-        const int jl1 = static_cast<int>(min(static_cast<long long>(a.n_jt), jl0 + rem));
+        const int jl1 = static_cast<int>(min(static_cast<long long>(upb), jl0 + rem));
 
         // ---- this thread's i-pairs (read straight from the packed records) ----
         const long long ig_block = a.i_begin + static_cast<long long>(ib) * IB;
@@ -486,7 +491,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
 #pragma unroll
         for (int e = 0; e < 4 * 2 * NP; ++e) run[e * THREADS + tid] = run_t(0);
 
-        for (int jl = jl0; jl < jl1; ++jl, ++k) {
+        for (int v = jl0; v < jl1; ++v, ++k) {
+            const int jl = v >> sl;                       // tile of this unit
+            const int jb = (v - (jl << sl)) * plen;       // and the part of it: j-particles [jb, jb + plen)
+            const int je = jb + plen;
             if (!DEC) {
                 __syncthreads();   // everyone is done with tile k-1 -> its stage may be refilled
                 if (tid == 0 && k + STAGES - 1 < n_units) issue(k + STAGES - 1);
@@ -504,22 +512,22 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
             if (KID == NB_KERNEL_SPLINE && !masked) {
                 if (um) {
                     m_fold = meta.y;
-                    tile_f32_spline<MODE, true, NP>(stage, S, eps2, meta.z);
+                    tile_f32_spline<MODE, true, NP>(stage, S, eps2, meta.z, jb, je);
                 } else {
-                    tile_f32_spline<MODE, false, NP>(stage, S, eps2, meta.z);
+                    tile_f32_spline<MODE, false, NP>(stage, S, eps2, meta.z, jb, je);
                 }
             } else if (masked) {
                 IState<NP> T = S;
-                tile_f32_masked<KID, MODE, NP, JUF>(stage, &T, eps2, jg0, ig0, a.n_j);
+                tile_f32_masked<KID, MODE, NP, JUF>(stage, &T, eps2, jg0, ig0, a.n_j, jb, je);
                 S = T;
             } else if (um && uc) {
                 m_fold = meta.y;
-                tile_f32<KID, MODE, false, true, true, NP, JUF>(stage, S, eps2, meta.x, jg0, ig0, a.n_j);
+                tile_f32<KID, MODE, false, true, true, NP, JUF>(stage, S, eps2, meta.x, jg0, ig0, a.n_j, jb, je);
             } else if (um) {
                 m_fold = meta.y;
-                tile_f32<KID, MODE, false, true, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
+                tile_f32<KID, MODE, false, true, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j, jb, je);
             } else {
-                tile_f32<KID, MODE, false, false, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j);
+                tile_f32<KID, MODE, false, false, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j, jb, je);
             }
 
             // fold this tile's f32 partials (x tile mass) into the running sums
@@ -552,7 +560,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
         }
 
         // ---- write this segment's partial sums ----
-        const bool is_full = (jl0 == 0 && jl1 == a.n_jt);
+        const bool is_full = (jl0 == 0 && jl1 == upb);
         const size_t base  = is_full ? static_cast<size_t>(ib) * IB
                                      : (static_cast<size_t>(cta) * 2 + (u == u0 ? 0 : 1)) * IB;
 #pragma unroll

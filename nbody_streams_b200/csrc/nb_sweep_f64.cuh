@@ -88,7 +88,8 @@ struct IState64 {
 template <int KID, int MODE, bool MASK, bool UM, bool UC, int NI>
 __device__ __forceinline__ void tile_f64(const unsigned char* __restrict__ stage, IState64<NI>& S,
                                          const double eps2, const double c_tile, const long long jg0,
-                                         const long long ig0, const long long n_j) {
+                                         const long long ig0, const long long n_j, const int jb = 0,
+                                         const int je = TJ) {
     const double* __restrict__ sX = reinterpret_cast<const double*>(stage) + COMP_X * TJ;
     const double* __restrict__ sY = reinterpret_cast<const double*>(stage) + COMP_Y * TJ;
     const double* __restrict__ sZ = reinterpret_cast<const double*>(stage) + COMP_Z * TJ;
@@ -98,7 +99,7 @@ __device__ __forceinline__ void tile_f64(const unsigned char* __restrict__ stage
 #pragma unroll
     for (int q = 0; q < NI; ++q) cmax[q] = UC ? fmax(c_tile, S.c[q]) : 0.0;
 #pragma unroll 1
-    for (int j0 = 0; j0 < TJ; j0 += 2) {
+    for (int j0 = jb; j0 < je; j0 += 2) {   // [jb, je): the whole tile, or one part of it (sub-tile work units)
         const double2 x2 = *reinterpret_cast<const double2*>(sX + j0);
         const double2 y2 = *reinterpret_cast<const double2*>(sY + j0);
         const double2 z2 = *reinterpret_cast<const double2*>(sZ + j0);
@@ -158,7 +159,8 @@ __device__ __forceinline__ void spline_exact_f64(const double xj, const double y
 
 template <int MODE, bool UM, int NI>
 __device__ __forceinline__ void tile_f64_spline(const unsigned char* __restrict__ stage, IState64<NI>& S,
-                                                const double eps2, const double c_max_tile) {
+                                                const double eps2, const double c_max_tile, const int jb = 0,
+                                                const int je = TJ) {
     const double* __restrict__ sX = reinterpret_cast<const double*>(stage) + COMP_X * TJ;
     const double* __restrict__ sY = reinterpret_cast<const double*>(stage) + COMP_Y * TJ;
     const double* __restrict__ sZ = reinterpret_cast<const double*>(stage) + COMP_Z * TJ;
@@ -170,7 +172,7 @@ __device__ __forceinline__ void tile_f64_spline(const unsigned char* __restrict_
     const int hi_lim = __double2hiint(h2max);   // d may be inside only if hiword(d) <= hiword(h2max)
 
 #pragma unroll 1
-    for (int j0 = 0; j0 < TJ; j0 += 2) {
+    for (int j0 = jb; j0 < je; j0 += 2) {
         const double2 x2 = *reinterpret_cast<const double2*>(sX + j0);
         const double2 y2 = *reinterpret_cast<const double2*>(sY + j0);
         const double2 z2 = *reinterpret_cast<const double2*>(sZ + j0);
@@ -239,9 +241,12 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
     }
     __syncthreads();
 
+    const int sl   = a.split_log2;
+    const int upb  = a.n_jt << sl;              // work units per i-block
+    const int plen = TJ >> sl;                  // j-particles per unit
     auto issue = [&](int k) {
         const long long u = u0 + k;
-        const int jl      = static_cast<int>(u % a.n_jt);
+        const int jl      = static_cast<int>(u % upb) >> sl;
         const int gt      = local_to_global_tile(a, jl);
         uint64_t* bar     = &full_bar[k % STAGES];
         mbar_expect_tx(bar, TILE_BYTES_F64);
@@ -255,10 +260,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
     long long u = u0;
     int k = 0;
     while (u < u1) {
-        const int ib  = static_cast<int>(u / a.n_jt);
-        const int jl0 = static_cast<int>(u - static_cast<long long>(ib) * a.n_jt);
+        const int ib  = static_cast<int>(u / upb);
+        const int jl0 = static_cast<int>(u - static_cast<long long>(ib) * upb);
         const long long rem = u1 - u;
-        const int jl1 = static_cast<int>(min(static_cast<long long>(a.n_jt), jl0 + rem));
+        const int jl1 = static_cast<int>(min(static_cast<long long>(upb), jl0 + rem));
 
         const long long ig_block = a.i_begin + static_cast<long long>(ib) * IB;
         const long long ig0      = ig_block + tid;
@@ -282,7 +287,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
 #pragma unroll
         for (int e = 0; e < 4 * NI; ++e) run[e * THREADS + tid] = 0.0;
 
-        for (int jl = jl0; jl < jl1; ++jl, ++k) {
+        for (int v = jl0; v < jl1; ++v, ++k) {
+            const int jl = v >> sl;                       // tile of this unit
+            const int jb = (v - (jl << sl)) * plen;       // and the part of it: j-particles [jb, jb + plen)
+            const int je = jb + plen;
             __syncthreads();
             if (tid == 0 && k + STAGES - 1 < n_units) issue(k + STAGES - 1);
             mbar_wait(&full_bar[k % STAGES], (k / STAGES) & 1);
@@ -298,20 +306,20 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
                 // two-phase spline needs an upper bound of the tile's h^2: available when the tile is uniform
                 if (um) {
                     m_fold = meta.y;
-                    tile_f64_spline<MODE, true, NI>(stage, S, eps2, meta.x);
+                    tile_f64_spline<MODE, true, NI>(stage, S, eps2, meta.x, jb, je);
                 } else {
-                    tile_f64_spline<MODE, false, NI>(stage, S, eps2, meta.x);
+                    tile_f64_spline<MODE, false, NI>(stage, S, eps2, meta.x, jb, je);
                 }
             } else if (masked) {
-                tile_f64<KID, MODE, true, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j);
+                tile_f64<KID, MODE, true, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j, jb, je);
             } else if (um && uc) {
                 m_fold = meta.y;
-                tile_f64<KID, MODE, false, true, true, NI>(stage, S, eps2, meta.x, jg0, ig0, a.n_j);
+                tile_f64<KID, MODE, false, true, true, NI>(stage, S, eps2, meta.x, jg0, ig0, a.n_j, jb, je);
             } else if (um) {
                 m_fold = meta.y;
-                tile_f64<KID, MODE, false, true, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j);
+                tile_f64<KID, MODE, false, true, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j, jb, je);
             } else {
-                tile_f64<KID, MODE, false, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j);
+                tile_f64<KID, MODE, false, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j, jb, je);
             }
             // fold the tile's partial sums (x tile mass) into the running sums in shared memory
 #pragma unroll
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
             }
         }
 
-        const bool is_full = (jl0 == 0 && jl1 == a.n_jt);
+        const bool is_full = (jl0 == 0 && jl1 == upb);
         const size_t base  = is_full ? static_cast<size_t>(ib) * IB
                                      : (static_cast<size_t>(cta) * 2 + (u == u0 ? 0 : 1)) * IB;
         double4* dst = reinterpret_cast<double4*>(is_full ? a.full : a.part) + base;
