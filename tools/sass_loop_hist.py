@@ -1,11 +1,13 @@
 #!/usr/bin/env python3
 """Histogram the opcodes of the hottest loop of each kernel in a cubin / .so.
 
-Usage: sass_loop_hist.py <file> [name-substring] [--key OPC]
+Usage: sass_loop_hist.py <file> [name-substring] [--key OPC] [--all OPC]
 Finds backward branches in `cuobjdump -sass` output, takes the loop body
 [target, branch] with the most `--key` opcodes (default FFMA2, falls back to
 DFMA/FFMA) and prints the opcode histogram, so the per-interaction issue-slot
-budget can be checked without a GPU.
+budget can be checked without a GPU.  `--all OPC` prints EVERY innermost loop
+that contains OPC instead (kernels with several tile paths: the uniform fast
+path, the general per-particle path, the exact spline step).
 """
 import re
 import subprocess
@@ -41,8 +43,24 @@ def main():
     key = None
     if "--key" in sys.argv:
         key = sys.argv[sys.argv.index("--key") + 1]
+    every = sys.argv[sys.argv.index("--all") + 1] if "--all" in sys.argv else None
     for name, rows in kernels(path):
         if sub not in name:
+            continue
+        if every:
+            print(f"== {name}")
+            loops = []
+            for addr, ins in rows:
+                m = re.search(r"0x([0-9a-f]+)\s*$", ins) if "BRA" in ins else None
+                if m and int(m.group(1), 16) < addr:
+                    loops.append((int(m.group(1), 16), addr))
+            for tgt, addr in loops:
+                if any(t2 >= tgt and a2 <= addr and (t2, a2) != (tgt, addr) for t2, a2 in loops):
+                    continue                                  # not innermost
+                c = Counter(opcode(i) for a, i in rows if tgt <= a <= addr)
+                if c[every]:
+                    print(f"   loop 0x{tgt:x}..0x{addr:x}: {sum(c.values())} instr")
+                    print("      " + "  ".join(f"{o}:{n}" for o, n in c.most_common()))
             continue
         best = None
         for addr, ins in rows:
