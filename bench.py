@@ -385,7 +385,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt_e2e = float(t.item())
         e2e = {"value": n_e2e * float(N) * float(N) / dt_e2e, "unit": "interactions/s",
-               "h2d_bytes_per_step": int(pos_host.nbytes), "d2h_bytes_per_step": int(acc.nbytes + phi.nbytes),
+               # per rank: with several ranks each uploads only the rows of its shard (the packed records of the
+               # other shards arrive over NVLink) and every rank downloads the full result (gather='all')
+               "h2d_bytes_per_step": int(pos_host.nbytes // world), "d2h_bytes_per_step": int(acc.nbytes + phi.nbytes),
                "ms_per_call": dt_e2e / n_e2e * 1e3, "calls": n_e2e,
                "api": "compute_nbody_forces_potential_gpu(numpy pos, scalar mass, scalar softening) -> numpy"}
 

@@ -230,18 +230,22 @@ def _dt_code(t) -> int:
     raise ValueError(f"unsupported dtype {t.dtype}")
 
 
-def _device_operand(arr_cpu, scalar, original, dtype_t, device):
-    """-> (tensor or None, scalar): host array -> H2D, device array -> as is, scalar -> broadcast in the pack kernel."""
+def _device_operand(arr_cpu, scalar, original, dtype_t, device, rows=slice(None)):
+    """-> (tensor or None, scalar): host array -> H2D, device array -> as is, scalar -> broadcast in the pack kernel
+    (`rows`: only these rows of an array operand)."""
     import torch
 
     if scalar is not None:
         return None, float(scalar)
     if arr_cpu is not None:
-        return torch.from_numpy(np.ascontiguousarray(arr_cpu)).to(device), 0.0
-    t = _as_cuda_tensor(original, device)
+        return torch.from_numpy(np.ascontiguousarray(arr_cpu[rows])).to(device), 0.0
+    t = _as_cuda_tensor(original, device)[rows]
     if t.dtype not in (torch.float32, torch.float64):
         t = t.to(dtype_t)
     return t.contiguous(), 0.0
+
+
+_PINNED_SIZES_SEEN: set = set()
 
 
 def _to_host(t):
@@ -254,6 +258,15 @@ def _to_host(t):
     if t.numel() == 0:
         return t.cpu().numpy()
     try:
+        # Page-locking fresh memory costs ~1 ms/MB (cudaHostAlloc), far more than the copy itself, and the caller
+        # typically still holds the previous result when the next one is produced.  The first request of a size
+        # therefore pins three blocks and hands two straight back to torch's caching host allocator: later calls
+        # find a cached block as long as no more than two earlier results of that size are alive.
+        key = (t.dtype, tuple(t.shape))
+        if key not in _PINNED_SIZES_SEEN:
+            _PINNED_SIZES_SEEN.add(key)
+            spare = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for _ in range(2)]
+            del spare
         out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     except RuntimeError:
         return t.cpu().numpy()
@@ -263,7 +276,7 @@ def _to_host(t):
 
 
 def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, mode, G, eps2, dtype_np, group=None,
-                n_sources=None, algorithm=None, gather="all"):
+                n_sources=None, algorithm=None, gather="all", local_rows=False):
     """pack + sweep + finish on the current stream.  Returns (acc|None, phi|None) torch tensors.
 
     With a torch.distributed `group` of more than one rank every rank packs all N particles and evaluates its
@@ -273,12 +286,16 @@ def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, m
     full arrays; 'root' — only rank 0 of the group receives them (the others return their own rows);
     'local' — no gather, every rank returns the rows of its shard (``ShardLayout(N, world).rows(rank)``).
 
+    `local_rows`: pos_t / mass_t / h_t hold only this rank's rows; each rank packs its own shard and the packed
+    shards are all-gathered (otherwise every rank packs all N from full arrays).
+
     `n_sources` (None = N): only the j-tiles holding particles [0, n_sources) are swept, i.e. the first
     n_sources particles are the sources and all N are targets.  The caller passes zero masses for the
     particles >= n_sources (the tile straddling n_sources is swept whole)."""
     import torch
 
-    from .engine import ShardLayout, gather_rows_padded, group_info, reduce_scatter_shards, sym_plan
+    from .engine import (ShardLayout, allgather_shards, gather_rows_padded, group_info, reduce_scatter_shards,
+                         sym_plan)
 
     if gather not in ("all", "root", "local"):
         raise ValueError(f"gather must be 'all', 'root' or 'local', got {gather!r}")
@@ -319,9 +336,16 @@ def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, m
                                      float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, float(G), float(eps2),
                                      packed.data_ptr(), ws.data_ptr(), ws_bytes, grid, acc_ptr, phi_ptr, stream))
         else:
-            _lib.check(lib.nb_pack(prec, kernel_id, packed.data_ptr(), 0, pos_t.data_ptr(), _dt_code(pos_t),
-                                   mass_ptr, mass_dt, float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, n_slots,
-                                   float(eps2), stream))
+            if local_rows:
+                # own shard only (records [i_begin, i_begin + shard), padding included), then the exchange
+                _lib.check(lib.nb_pack(prec, kernel_id, packed.data_ptr(), i_begin, pos_t.data_ptr(), _dt_code(pos_t),
+                                       mass_ptr, mass_dt, float(mass_scalar), h_ptr, h_dt, float(h_scalar), n_i,
+                                       layout.shard, float(eps2), stream))
+                allgather_shards(packed, layout, rank, int(lib.nb_packed_bytes(prec, layout.shard)), group)
+            else:
+                _lib.check(lib.nb_pack(prec, kernel_id, packed.data_ptr(), 0, pos_t.data_ptr(), _dt_code(pos_t),
+                                       mass_ptr, mass_dt, float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, n_slots,
+                                       float(eps2), stream))
             if sym:
                 ws_bytes = lib.nb_sym_workspace_bytes(n_slots)
                 ws = _scratch(device, "workspace", ws_bytes)
@@ -374,9 +398,20 @@ def _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, device):
     return m, 0.0, n_src
 
 
-def _prepare(pos, mass, softening, precision, kernel, skip_validation, device):
-    """Common front end of the two public calls -> device operands."""
+def _prepare(pos, mass, softening, precision, kernel, skip_validation, device, group=None, n_sources=None):
+    """Common front end of the public calls -> device operands (+ `local`: the operands hold only the rows of
+    this rank's shard).  With a multi-rank `group` each rank uploads / keeps only its own rows: the packed
+    records of the other shards arrive through the all-gather over NVLink instead of world x redundant PCIe
+    copies (not with n_sources, whose mass masking needs the full arrays)."""
     import torch
+
+    from .engine import ShardLayout, group_info
+
+    rank, world = group_info(group) if group is not None else (0, 1)
+    local = world > 1 and n_sources is None
+
+    def rows_of(N):
+        return ShardLayout(N, world).rows(rank)
 
     if skip_validation:
         # Hot-loop path (reference fields.py:790-799): trust device arrays of the right dtype.
@@ -384,11 +419,17 @@ def _prepare(pos, mass, softening, precision, kernel, skip_validation, device):
         prec, dtype_np = _PRECISION_MAP[prec_key]
         kernel_id = KERNEL_MAP[kernel.lower()]
         dev = device or (pos.device if hasattr(pos, "device") and isinstance(pos, torch.Tensor) else torch.device("cuda", torch.cuda.current_device()))
-        pos_t = _as_cuda_tensor(pos, dev).contiguous()
+        pos_t = _as_cuda_tensor(pos, dev)
         N = pos_t.shape[0]
-        mass_t, mass_s = (None, float(mass)) if np.isscalar(mass) else (_as_cuda_tensor(mass, dev).contiguous(), 0.0)
-        h_t, h_s = (None, float(softening)) if np.isscalar(softening) else (_as_cuda_tensor(softening, dev).contiguous(), 0.0)
-        return pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np
+        mass_t, mass_s = (None, float(mass)) if np.isscalar(mass) else (_as_cuda_tensor(mass, dev), 0.0)
+        h_t, h_s = (None, float(softening)) if np.isscalar(softening) else (_as_cuda_tensor(softening, dev), 0.0)
+        if local:
+            r = rows_of(N)
+            pos_t = pos_t[r]
+            mass_t = mass_t[r] if mass_t is not None else None
+            h_t = h_t[r] if h_t is not None else None
+        cont = lambda t: t.contiguous() if t is not None else None  # noqa: E731
+        return pos_t.contiguous(), cont(mass_t), mass_s, cont(h_t), h_s, N, prec, kernel_id, dtype_np, local
 
     v = _validate_inputs(pos, mass, softening, precision, kernel)
     dtype_np = v["dtype_np"]
@@ -398,16 +439,17 @@ def _prepare(pos, mass, softening, precision, kernel, skip_validation, device):
             device = pos.device
         else:
             device = torch.device("cuda", torch.cuda.current_device())
+    r = rows_of(v["N"]) if local else slice(None)
     if v["pos_cpu"] is None:
-        pos_t = _as_cuda_tensor(v["original_pos"], device)
+        pos_t = _as_cuda_tensor(v["original_pos"], device)[r]
         if pos_t.dtype not in (torch.float32, torch.float64):
             pos_t = pos_t.to(dtype_t)
         pos_t = pos_t.contiguous()
     else:
-        pos_t = torch.from_numpy(np.ascontiguousarray(v["pos_cpu"])).to(device)
-    mass_t, mass_s = _device_operand(v["mass_cpu"], v["mass_scalar"], v["original_mass"], dtype_t, device)
-    h_t, h_s = _device_operand(v["h_cpu"], v["h_scalar"], v["original_h"], dtype_t, device)
-    return pos_t, mass_t, mass_s, h_t, h_s, v["N"], v["prec"], v["kernel_id"], dtype_np
+        pos_t = torch.from_numpy(np.ascontiguousarray(v["pos_cpu"][r])).to(device)
+    mass_t, mass_s = _device_operand(v["mass_cpu"], v["mass_scalar"], v["original_mass"], dtype_t, device, r)
+    h_t, h_s = _device_operand(v["h_cpu"], v["h_scalar"], v["original_h"], dtype_t, device, r)
+    return pos_t, mass_t, mass_s, h_t, h_s, v["N"], v["prec"], v["kernel_id"], dtype_np, local
 
 
 # ---------------------------------------------------------------------------
@@ -457,11 +499,11 @@ def compute_nbody_forces_gpu(
     bad shapes, precision or kernel names, RuntimeError for CUDA failures.
     """
     _torch()
-    ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
-    pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
+    ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device, group, n_sources)
+    pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np, local = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
     mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
-    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np, group, n_src, algorithm, gather)
+    acc, _ = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_FORCE, G, e2, dtype_np, group, n_src, algorithm, gather, local)
     if return_cupy:
         return acc.as_subclass(DeviceArray)
     return _to_host(acc)
@@ -492,11 +534,11 @@ def compute_nbody_potential_gpu(
     (fields.py:280-288) — see DESIGN.md.
     """
     _torch()
-    ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
-    pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
+    ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device, group, n_sources)
+    pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np, local = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
     mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
-    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np, group, n_src, algorithm, gather)
+    _, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_POT, G, e2, dtype_np, group, n_src, algorithm, gather, local)
     if return_cupy:
         return phi.as_subclass(DeviceArray)
     return _to_host(phi)
@@ -522,11 +564,11 @@ def compute_nbody_forces_potential_gpu(
     """Accelerations AND potential from one fused sweep (new; the reference needs two
     O(N^2) passes, run.py:611-634).  Returns ``(acc (N,3), phi (N,))``."""
     _torch()
-    ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device)
-    pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np = ops
+    ops = _prepare(pos, mass, softening, precision, kernel, skip_validation, device, group, n_sources)
+    pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, dtype_np, local = ops
     e2 = EPS2_DEFAULT[precision.lower()] if eps2 is None else float(eps2)
     mass_t, mass_s, n_src = _limit_sources(mass_t, mass_s, N, n_sources, dtype_np, pos_t.device)
-    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np, group, n_src, algorithm, gather)
+    acc, phi = _run_direct(pos_t, mass_t, mass_s, h_t, h_s, N, prec, kernel_id, MODE_BOTH, G, e2, dtype_np, group, n_src, algorithm, gather, local)
     if return_cupy:
         return acc.as_subclass(DeviceArray), phi.as_subclass(DeviceArray)
     return _to_host(acc), _to_host(phi)
