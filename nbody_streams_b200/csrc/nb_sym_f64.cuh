@@ -18,6 +18,10 @@ constexpr int SYM_NI_F64     = 4;                       // i-particles per threa
 constexpr int SYM_IB_F64     = THREADS * SYM_NI_F64;    // 512 per CTA
 constexpr int SYM_TPB_F64    = SYM_IB_F64 / TJ;         // 2 tiles per i-block
 constexpr int SYM_STAGES_F64 = 2;                       // a tile takes ~40k cycles to sweep: one tile of prefetch is plenty
+#ifndef NB_SYM_UNROLL_F64
+#define NB_SYM_UNROLL_F64 2
+#endif
+constexpr int SYM_UNROLL_F64 = NB_SYM_UNROLL_F64;       // rotation steps per loop iteration (non-spline kernels)
 
 __device__ __forceinline__ double shfl_d(const double v, const int src) {
     int lo = __double2loint(v), hi = __double2hiint(v);
@@ -126,6 +130,7 @@ __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ s
     const double* __restrict__ sM = reinterpret_cast<const double*>(stage) + COMP_M * TJ;
     const double* __restrict__ sC = reinterpret_cast<const double*>(stage) + COMP_C * TJ;
     constexpr bool kUsesC = (KID == NB_KERNEL_PLUMMER || KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
+    constexpr int kUnroll = (KID == 4 /* spline: the exact step's state copy */) ? 1 : SYM_UNROLL_F64;
     const int src = (lane + 1) & 31;
 
 #pragma unroll 1
@@ -133,7 +138,7 @@ __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ s
         JAcc64 J;
         J.x = J.y = J.z = J.p = 0.0;
         const int jb = 32 * rho;
-#pragma unroll 1
+#pragma unroll kUnroll
         for (int s = 0; s < 32; ++s) {
             const int jj    = jb + ((lane + s) & 31);
             const double xj = sX[jj], yj = sY[jj], zj = sZ[jj];
