@@ -46,14 +46,19 @@ inline int run_kernel(K kern, int smem, int op, const SweepArgs* a, int grid, in
 template <int KID, int MODE, int ACC, int V>
 inline int run_f32(int op, const SweepArgs* a, int grid, int* out, cudaStream_t st) {
     constexpr VariantF32 v = variant_f32(V);
-    return run_kernel(sweep_f32_kernel<KID, MODE, ACC, v.np, v.minb, v.ju, v.dec>, SweepF32Smem<v.np, ACC>::kTotal, op, a, grid,
-                      out, st);
+    if (op == OP_LAUNCH && a->split_log2 > 0)      // sub-tile work units: separate instantiation (same blocking)
+        return run_kernel(sweep_f32_kernel<KID, MODE, ACC, v.np, v.minb, v.ju, v.dec, true>,
+                          SweepF32Smem<v.np, ACC>::kTotal, op, a, grid, out, st);
+    return run_kernel(sweep_f32_kernel<KID, MODE, ACC, v.np, v.minb, v.ju, v.dec, false>, SweepF32Smem<v.np, ACC>::kTotal,
+                      op, a, grid, out, st);
 }
 template <int KID, int MODE, int V>
 inline int run_f64(int op, const SweepArgs* a, int grid, int* out, cudaStream_t st) {
     constexpr VariantF64 v = variant_f64(V);
-    return run_kernel(sweep_f64_kernel<KID, MODE, v.ni, v.minb>, STAGES * TILE_BYTES_F64 + 64 + 4 * v.ni * THREADS * 8, op, a,
-                      grid, out, st);
+    constexpr int smem = STAGES * TILE_BYTES_F64 + 64 + 4 * v.ni * THREADS * 8;
+    if (op == OP_LAUNCH && a->split_log2 > 0)
+        return run_kernel(sweep_f64_kernel<KID, MODE, v.ni, v.minb, true>, smem, op, a, grid, out, st);
+    return run_kernel(sweep_f64_kernel<KID, MODE, v.ni, v.minb, false>, smem, op, a, grid, out, st);
 }
 
 template <int KID, int MODE, int ACC, bool ALLV>

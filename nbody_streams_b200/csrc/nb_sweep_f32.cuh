@@ -415,7 +415,8 @@ struct SweepF32Smem {
 //   DEC = true : warps run decoupled — every warp arrives on the stage's "empty" mbarrier when it is
 //                done with a tile and the LAST warp out (pending count 1) issues the TMA refill, so no
 //                thread ever waits for another warp except through data availability
-template <int KID, int MODE, int ACC, int NP, int MINB, int JUF = 4, bool DEC = false>
+//   SUB = true : sub-tile work units (a.split_log2 > 0, small N); SUB = false: whole tiles, constant loop bounds
+template <int KID, int MODE, int ACC, int NP, int MINB, int JUF = 4, bool DEC = false, bool SUB = false>
 __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     using L = SweepF32Smem<NP, ACC>;
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
     }
     __syncthreads();
 
-    const int sl  = a.split_log2;
+    const int sl  = SUB ? a.split_log2 : 0;
     const int upb = a.n_jt << sl;               // work units per i-block
     const int plen = TJ >> sl;                  // j-particles per unit
     auto issue = [&](int k) {   // elected thread: TMA bulk load of unit k's j-tile
@@ -509,26 +510,36 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f32_kernel(const SweepArg
             const bool uc = (meta.x == meta.x), um = (meta.y == meta.y);
             float m_fold = 1.f;
 
-            if (KID == NB_KERNEL_SPLINE && !masked) {
-                if (um) {
-                    m_fold = meta.y;
-                    tile_f32_spline<MODE, true, NP>(stage, S, eps2, meta.z, jb, je);
-                } else {
-                    tile_f32_spline<MODE, false, NP>(stage, S, eps2, meta.z, jb, je);
-                }
-            } else if (masked) {
-                IState<NP> T = S;
-                tile_f32_masked<KID, MODE, NP, JUF>(stage, &T, eps2, jg0, ig0, a.n_j, jb, je);
-                S = T;
-            } else if (um && uc) {
-                m_fold = meta.y;
-                tile_f32<KID, MODE, false, true, true, NP, JUF>(stage, S, eps2, meta.x, jg0, ig0, a.n_j, jb, je);
-            } else if (um) {
-                m_fold = meta.y;
-                tile_f32<KID, MODE, false, true, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j, jb, je);
+            // Whole tiles (the only case from a few 10^4 particles on) call the tile loops with CONSTANT bounds: the hot
+            // loops are sensitive to code generation (a run-time trip count cost 4-5 % at N = 1M, a second inlined
+            // copy in the same kernel up to 13 %), so the sub-tile case is a separate kernel instantiation (SUB).
+#define NB_TILE_DISPATCH_F32(JB, JE)                                                                                  \
+    if (KID == NB_KERNEL_SPLINE && !masked) {                                                                         \
+        if (um) {                                                                                                     \
+            m_fold = meta.y;                                                                                          \
+            tile_f32_spline<MODE, true, NP>(stage, S, eps2, meta.z, JB, JE);                                          \
+        } else {                                                                                                      \
+            tile_f32_spline<MODE, false, NP>(stage, S, eps2, meta.z, JB, JE);                                         \
+        }                                                                                                             \
+    } else if (masked) {                                                                                              \
+        IState<NP> T = S;                                                                                             \
+        tile_f32_masked<KID, MODE, NP, JUF>(stage, &T, eps2, jg0, ig0, a.n_j, jb, je);                                \
+        S = T;                                                                                                        \
+    } else if (um && uc) {                                                                                            \
+        m_fold = meta.y;                                                                                              \
+        tile_f32<KID, MODE, false, true, true, NP, JUF>(stage, S, eps2, meta.x, jg0, ig0, a.n_j, JB, JE);             \
+    } else if (um) {                                                                                                  \
+        m_fold = meta.y;                                                                                              \
+        tile_f32<KID, MODE, false, true, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j, JB, JE);               \
+    } else {                                                                                                          \
+        tile_f32<KID, MODE, false, false, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j, JB, JE);              \
+    }
+            if constexpr (!SUB) {
+                NB_TILE_DISPATCH_F32(0, TJ)
             } else {
-                tile_f32<KID, MODE, false, false, false, NP, JUF>(stage, S, eps2, 0.f, jg0, ig0, a.n_j, jb, je);
+                NB_TILE_DISPATCH_F32(jb, je)
             }
+#undef NB_TILE_DISPATCH_F32
 
             // fold this tile's f32 partials (x tile mass) into the running sums
             const run_t mf = static_cast<run_t>(m_fold);

@@ -220,7 +220,7 @@ __device__ __forceinline__ void tile_f64_spline(const unsigned char* __restrict_
     }
 }
 
-template <int KID, int MODE, int NI, int MINB>
+template <int KID, int MODE, int NI, int MINB, bool SUB = false>
 __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int IB = THREADS * NI;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
     }
     __syncthreads();
 
-    const int sl   = a.split_log2;
+    const int sl   = SUB ? a.split_log2 : 0;   // SUB: sub-tile work units (small N), a separate instantiation
     const int upb  = a.n_jt << sl;              // work units per i-block
     const int plen = TJ >> sl;                  // j-particles per unit
     auto issue = [&](int k) {
@@ -302,25 +302,33 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_f64_kernel(const SweepArg
             const double2 meta = *reinterpret_cast<const double2*>(stage + 5 * TJ * 8);   // {c_uni, m_uni} or NaN
             const bool uc = (meta.x == meta.x), um = (meta.y == meta.y);
             double m_fold = 1.0;
-            if (KID == NB_KERNEL_SPLINE && !masked && uc) {
-                // two-phase spline needs an upper bound of the tile's h^2: available when the tile is uniform
-                if (um) {
-                    m_fold = meta.y;
-                    tile_f64_spline<MODE, true, NI>(stage, S, eps2, meta.x, jb, je);
-                } else {
-                    tile_f64_spline<MODE, false, NI>(stage, S, eps2, meta.x, jb, je);
-                }
-            } else if (masked) {
-                tile_f64<KID, MODE, true, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j, jb, je);
-            } else if (um && uc) {
-                m_fold = meta.y;
-                tile_f64<KID, MODE, false, true, true, NI>(stage, S, eps2, meta.x, jg0, ig0, a.n_j, jb, je);
-            } else if (um) {
-                m_fold = meta.y;
-                tile_f64<KID, MODE, false, true, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j, jb, je);
+            // constant bounds for whole tiles, a second inlined copy for sub-tile units (see nb_sweep_f32.cuh)
+#define NB_TILE_DISPATCH_F64(JB, JE)                                                                                  \
+    if (KID == NB_KERNEL_SPLINE && !masked && uc) {                                                                   \
+        /* two-phase spline needs an upper bound of the tile's h^2: available when the tile is uniform */             \
+        if (um) {                                                                                                     \
+            m_fold = meta.y;                                                                                          \
+            tile_f64_spline<MODE, true, NI>(stage, S, eps2, meta.x, JB, JE);                                          \
+        } else {                                                                                                      \
+            tile_f64_spline<MODE, false, NI>(stage, S, eps2, meta.x, JB, JE);                                         \
+        }                                                                                                             \
+    } else if (masked) {                                                                                              \
+        tile_f64<KID, MODE, true, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j, JB, JE);                    \
+    } else if (um && uc) {                                                                                            \
+        m_fold = meta.y;                                                                                              \
+        tile_f64<KID, MODE, false, true, true, NI>(stage, S, eps2, meta.x, jg0, ig0, a.n_j, JB, JE);                  \
+    } else if (um) {                                                                                                  \
+        m_fold = meta.y;                                                                                              \
+        tile_f64<KID, MODE, false, true, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j, JB, JE);                    \
+    } else {                                                                                                          \
+        tile_f64<KID, MODE, false, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j, JB, JE);                   \
+    }
+            if constexpr (!SUB) {
+                NB_TILE_DISPATCH_F64(0, TJ)
             } else {
-                tile_f64<KID, MODE, false, false, false, NI>(stage, S, eps2, 0.0, jg0, ig0, a.n_j, jb, je);
+                NB_TILE_DISPATCH_F64(jb, je)
             }
+#undef NB_TILE_DISPATCH_F64
             // fold the tile's partial sums (x tile mass) into the running sums in shared memory
 #pragma unroll
             for (int q = 0; q < NI; ++q) {

@@ -287,16 +287,21 @@ def test_failed_async_write_stops_the_run_and_keeps_a_restart(nb, tmp_path, monk
 
     monkeypatch.setattr(run_mod, "_save_restart", flaky)
     xv, m = nb.make_plummer_sphere(2000, M_total=1e9, a=1.0, seed=5)
-    kw = dict(precision="float64", kernel="spline", save_snapshots=False, verbose=False, restart_interval=4)
+    # a step takes ~40 us here and the failing job runs in the writer thread, so the run must be long enough for the
+    # failure to be noticed in the middle of it: 20000 steps, first restart write (the failing one) at step 50
+    steps, dt = 20_000, 1e-6
+    kw = dict(precision="float64", kernel="spline", save_snapshots=False, verbose=False, restart_interval=50)
     with pytest.raises(OSError, match="simulated"):
-        nb.run_nbody_gpu(xv, m, 0.0, 40e-4, 1e-4, 0.05, output_dir=str(tmp_path), **kw)
+        nb.run_nbody_gpu(xv, m, 0.0, steps * dt, dt, 0.05, output_dir=str(tmp_path), **kw)
     r = np.load(tmp_path / "restart.npz")
-    assert 4 <= int(r["step"]) < 40             # stopped long before the end, at a step boundary
+    stopped = int(r["step"])
+    assert 50 <= stopped < steps                # stopped long before the end, at a step boundary
     assert not (tmp_path / "restart.tmp.npz").exists()
     # the state in the file is the state of that step: continuing from it reproduces the uninterrupted run
     monkeypatch.setattr(run_mod, "_save_restart", real)
-    full = nb.run_nbody_gpu(xv, m, 0.0, 40e-4, 1e-4, 0.05, output_dir=str(tmp_path / "full"), **kw)
-    resumed = nb.run_nbody_gpu(xv, m, 0.0, 40e-4, 1e-4, 0.05, output_dir=str(tmp_path), continue_run=True, **kw)
+    short = stopped + 100
+    full = nb.run_nbody_gpu(xv, m, 0.0, short * dt, dt, 0.05, output_dir=str(tmp_path / "full"), **kw)
+    resumed = nb.run_nbody_gpu(xv, m, 0.0, short * dt, dt, 0.05, output_dir=str(tmp_path), continue_run=True, **kw)
     assert np.abs(resumed - full).max() / np.abs(full).max() < 1e-13
 
 
