@@ -200,11 +200,10 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
             mn = sM[j1]; cn = sC[j1];
         }
     }
+    static_assert(KID != NB_KERNEL_SPLINE, "the spline has its own, non-pipelined loop: sym_tile_f32_spline");
     f2 dx[NP], dy[NP], dz[NP], rinv[NP], h2[NP];
-    bool exact = false;
     // separations, softening term, r^2 and reciprocal square roots of the step whose record is (xj.., cj)
     auto prepare = [&]() {
-        float dmin = 3.0e38f;
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             dx[q] = sub2(splat(xj), S.x[q]);
@@ -220,12 +219,8 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
             const f2 d = fma2(dx[q], dx[q], fma2(dy[q], dy[q], fma2(dz[q], dz[q], c)));
             float d0, d1;
             upk(d, d0, d1);
-            if (KID == NB_KERNEL_SPLINE) dmin = fminf(dmin, fminf(d0, d1));
             rinv[q] = pk(rsqrt_approx(d0), rsqrt_approx(d1));
         }
-        // the spline is exactly Newtonian unless some pair of the step lies inside its softening length
-        // (rare): then the whole step is redone with the reference's piecewise polynomial
-        if (KID == NB_KERNEL_SPLINE) exact = dmin < (U ? c_pair : fmaxf(cj, cmax_i));
     };
     prepare();
 
@@ -233,24 +228,7 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
     J.x = J.y = J.z = J.p = 0ull;
 #pragma unroll SYM_UNROLL
     for (int t = 0; t < TJ; ++t) {
-        if (exact) {
-            SymCold32<NP> T;
-#pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                T.S.x[q] = S.x[q]; T.S.y[q] = S.y[q]; T.S.z[q] = S.z[q];
-                T.S.ax[q] = S.ax[q]; T.S.ay[q] = S.ay[q]; T.S.az[q] = S.az[q]; T.S.sp[q] = S.sp[q];
-                T.S.c0[q] = U ? c_pair : ci0[q];
-                T.S.c1[q] = U ? c_pair : ci1[q];
-                T.m[q]    = U ? 0ull : mi[q];
-            }
-            T.J = J;
-            sym_spline_exact_step<MODE, U, NP>(&T, xj, yj, zj, mj, cj, eps2);
-#pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                S.ax[q] = T.S.ax[q]; S.ay[q] = T.S.ay[q]; S.az[q] = T.S.az[q]; S.sp[q] = T.S.sp[q];
-            }
-            J = T.J;
-        } else {
+        {
             // kernel factors (mass-less: w ~ 1/r^3, p ~ 1/r) applied to both sides
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
@@ -342,7 +320,9 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
 // softening term that can apply the step finishes on the branch-free Newtonian path; otherwise (rare) the
 // whole step is redone by sym_spline_exact_step with the reference's piecewise polynomial.  The exact path
 // works on a copy of the thread state, which costs registers when several steps are in flight: measured best
-// with one step per iteration and the three phases in program order.
+// with one step per iteration and the three phases in program order (round-2 experiments, N = 262144 force:
+// this loop 21.4 ms; the software-pipelined loop with the exact step moved out of line through workspace atomics
+// 23.3-24.8 ms at 1, 2 or 4 steps per iteration; this loop with that out-of-line step 24.8 ms).
 // ---------------------------------------------------------------------------
 template <int MODE, bool U, int NP, typename ST>
 __device__ __forceinline__ void sym_tile_f32_spline(const unsigned char* __restrict__ stage, ST& S, const f2* mi,

@@ -51,4 +51,4 @@ for mode, mn in ((1, "force"), (3, "force+pot")):
     rows.append(f"| C5 dark 1.6M + star 400k + BH | {len(pos)} | float32 | spline | {mn} | {ms:.3f} | {g:.0f} |")
 print("\n".join(rows))
 Path("gpurun_out").mkdir(exist_ok=True)
-Path("gpurun_out/config_bench.md").write_text("# One-GPU throughput of the other BASELINE configurations (round 1)\n\n" + "\n".join(rows) + "\n")
+Path("gpurun_out/config_bench.md").write_text("# One-GPU throughput of the other BASELINE configurations (round 2: pair-symmetric sweep; round 1 numbers in r01_config_bench_c2_c4_c5.md)\n\n" + "\n".join(rows) + "\n")
