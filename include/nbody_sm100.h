@@ -201,6 +201,15 @@ int nb_sym_sweep(int prec, int kernel_id, int mode,
 int nb_sym_finish(int prec, int mode, const void *workspace, long first, long n_i,
                   double G, void *acc, void *phi, void *stream);
 
+/* Multi-GPU: finish fused with the reduction of the partial sums over NVLink peer memory.  Every rank's
+ * nb_sym_sweep leaves partial sums for all particle slots in its own workspace; this call, on the owner of the
+ * slots [first, first+n_i), adds those rows from the n_peers (<= 8) workspaces in the HOST array
+ * peer_workspaces (mapped peer pointers, the caller's own included; fixed order = rank order), scales by G and
+ * writes acc / phi.  Replaces reduce-scatter + nb_sym_finish by one kernel.  The caller orders the ranks
+ * (barrier before: every rank's sweeps are done; barrier before the workspaces are cleared again). */
+int nb_sym_finish_peers(int prec, int mode, const void *const *peer_workspaces, int n_peers,
+                        long first, long n_i, double G, void *acc, void *phi, void *stream);
+
 /* pack + symmetric sweep of all pairs + finish; same arguments as nb_direct,
  * workspace of nb_sym_workspace_bytes(nb_padded_count(n)), grid from nb_sym_grid. */
 int nb_direct_sym(int prec, int kernel_id, int mode,

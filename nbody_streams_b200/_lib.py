@@ -52,6 +52,7 @@ SIGNATURES = {
     "nb_sym_sweep": (_i, [_i, _i, _i, _vp, _l, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _vp, _sz, _l, _i, _i,
                           _vp]),
     "nb_sym_finish": (_i, [_i, _i, _vp, _l, _l, _d, _vp, _vp, _vp]),
+    "nb_sym_finish_peers": (_i, [_i, _i, C.POINTER(_vp), _i, _l, _l, _d, _vp, _vp, _vp]),
     "nb_direct_sym": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _d, _vp, _i, _d, _l, _d, _d, _vp, _vp, _sz, _i, _vp, _vp,
                            _vp]),
     "nb_kick_drift_pack": (_i, [_i, _vp, _vp, _vp, _i, _vp, _vp, _l, _l, _d, _d, _vp]),

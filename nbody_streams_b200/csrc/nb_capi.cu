@@ -14,6 +14,8 @@ int nb_launch_finish(int prec, long long n_i, int grid, int IB, int n_sweeps, co
                      size_t slot_bytes, size_t part_off, double G, void* acc, void* phi, cudaStream_t st);
 int nb_launch_sym_finish(int prec, const void* ws, long long first, long long n_i, double G, void* acc, void* phi,
                          cudaStream_t st);
+int nb_launch_sym_finish_peers(int prec, const void* const* peer_ws, int n_peers, long long first, long long n_i,
+                               double G, void* acc, void* phi, cudaStream_t st);
 int nb_launch_kick_drift_pack(int prec, double* pos, double* vel, const void* acc, int acc_dt,
                               const double* acc_ext, void* packed, long long first, long long n, double dt_half,
                               double dt, cudaStream_t st);
@@ -391,6 +393,18 @@ int nb_sym_finish(int prec, int mode, const void* workspace, long first, long n_
     if (!(mode & NB_MODE_FORCE)) acc = nullptr;
     if (!(mode & NB_MODE_POT)) phi = nullptr;
     return nb_launch_sym_finish(prec, workspace, first, n_i, G, acc, phi, static_cast<cudaStream_t>(stream));
+}
+
+int nb_sym_finish_peers(int prec, int mode, const void* const* peer_workspaces, int n_peers, long first, long n_i,
+                        double G, void* acc, void* phi, void* stream) {
+    if (!valid_prec(prec) || !valid_mode(mode) || !peer_workspaces || n_peers < 1 || n_peers > 8 || first < 0 || n_i < 0)
+        return NB_E_INVALID_ARG;
+    for (int r = 0; r < n_peers; ++r)
+        if (!peer_workspaces[r]) return NB_E_INVALID_ARG;
+    if (!(mode & NB_MODE_FORCE)) acc = nullptr;
+    if (!(mode & NB_MODE_POT)) phi = nullptr;
+    return nb_launch_sym_finish_peers(prec, peer_workspaces, n_peers, first, n_i, G, acc, phi,
+                                      static_cast<cudaStream_t>(stream));
 }
 
 int nb_direct_sym(int prec, int kernel_id, int mode, const void* pos, int pos_dt, const void* mass, int mass_dt,

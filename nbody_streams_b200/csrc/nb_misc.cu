@@ -184,6 +184,43 @@ __global__ void sym_finish_kernel(const double4* __restrict__ ws, long long firs
     if (phi) phi[i] = static_cast<OT>(-G * v.w);
 }
 
+// Multi-GPU finish fused with the reduction of the partial sums (exchange = 'p2p'): every rank's symmetric sweep
+// leaves partial sums for ALL particle slots in its own workspace; the owner of a shard adds the rows of its shard
+// from every rank's workspace — its own and, over NVLink peer memory, the others' — in fixed rank order, scales and
+// writes acc / phi.  Replaces reduce-scatter + finish by ONE kernel; the caller brackets it with symmetric-memory
+// barriers (all sweeps done before, all reads done before the workspaces are cleared again).
+struct PeerWs {
+    const double4* p[8];
+    int count;
+};
+
+template <typename OT>
+__global__ void sym_finish_peers_kernel(const PeerWs peers, long long first, long long n_i, double G,
+                                        OT* __restrict__ acc, OT* __restrict__ phi) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_i) return;
+    double4 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)       // all loads in flight before the first add (peer latency ~2 us)
+        if (r < peers.count) v[r] = peers.p[r][first + i];
+    double sx = 0.0, sy = 0.0, sz = 0.0, sp = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (r < peers.count) {
+            sx += v[r].x;
+            sy += v[r].y;
+            sz += v[r].z;
+            sp += v[r].w;
+        }
+    }
+    if (acc) {
+        acc[3 * i + 0] = static_cast<OT>(G * sx);
+        acc[3 * i + 1] = static_cast<OT>(G * sy);
+        acc[3 * i + 2] = static_cast<OT>(G * sz);
+    }
+    if (phi) phi[i] = static_cast<OT>(-G * sp);
+}
+
 // ---------------------------------------------------------------------------
 // KDK pieces
 // ---------------------------------------------------------------------------
@@ -414,6 +451,24 @@ int nb_launch_sym_finish(int prec, const void* ws, long long first, long long n_
     else
         sym_finish_kernel<float><<<blocks, threads, 0, st>>>(w, first, n_i, G, static_cast<float*>(acc),
                                                              static_cast<float*>(phi));
+    NB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int nb_launch_sym_finish_peers(int prec, const void* const* peer_ws, int n_peers, long long first, long long n_i,
+                               double G, void* acc, void* phi, cudaStream_t st) {
+    if (n_i <= 0) return 0;
+    PeerWs pw;
+    pw.count = n_peers;
+    for (int r = 0; r < 8; ++r) pw.p[r] = r < n_peers ? static_cast<const double4*>(peer_ws[r]) : nullptr;
+    const int threads = 128;
+    const unsigned blocks = static_cast<unsigned>((n_i + threads - 1) / threads);
+    if (prec == NB_PREC_F64)
+        sym_finish_peers_kernel<double><<<blocks, threads, 0, st>>>(pw, first, n_i, G, static_cast<double*>(acc),
+                                                                    static_cast<double*>(phi));
+    else
+        sym_finish_peers_kernel<float><<<blocks, threads, 0, st>>>(pw, first, n_i, G, static_cast<float*>(acc),
+                                                                   static_cast<float*>(phi));
     NB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -30,7 +30,7 @@ constexpr int SYM_IB_F32      = THREADS * 2 * SYM_NP;    // 1024 i-particles per
 constexpr int SYM_TPB_F32     = SYM_IB_F32 / TJ;         // 4 tiles per i-block
 constexpr int SYM_FLUSH_TILES = 8;                       // i-side: float running sums -> double workspace
 #ifndef NB_SYM_UNROLL
-#define NB_SYM_UNROLL 4
+#define NB_SYM_UNROLL 8
 #endif
 constexpr int SYM_UNROLL = NB_SYM_UNROLL;                 // steps per iteration of the hot loop
 

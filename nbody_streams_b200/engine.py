@@ -328,9 +328,20 @@ class DirectEngine:
         """Workspace of 4 doubles per particle slot (all shards) + this rank's reduce-scatter output."""
         torch = self.torch
         if self._sym_ws is None:
-            self._sym_ws = torch.zeros((self.layout.n_slots, 4), dtype=torch.float64, device=self.device)
-            if self.world > 1:
-                self._sym_out = torch.zeros((self.layout.shard, 4), dtype=torch.float64, device=self.device)
+            if self.exchange == "p2p":
+                # the workspace lives in symmetric memory: the owner of a shard reads its rows from every rank's
+                # workspace over NVLink in the fused finish kernel (no reduce-scatter)
+                import torch.distributed._symmetric_memory as symm_mem
+
+                self._sym_ws = symm_mem.empty((self.layout.n_slots, 4), dtype=torch.float64, device=self.device)
+                self._sym_ws.zero_()
+                self._ws_symm = symm_mem.rendezvous(self._sym_ws, self.group if self.group is not None
+                                                    else _dist().group.WORLD)
+                self._ws_peer_ptrs = (C.c_void_p * self.world)(*[int(p) for p in self._ws_symm.buffer_ptrs])
+            else:
+                self._sym_ws = torch.zeros((self.layout.n_slots, 4), dtype=torch.float64, device=self.device)
+                if self.world > 1:
+                    self._sym_out = torch.zeros((self.layout.shard, 4), dtype=torch.float64, device=self.device)
         return self._sym_ws, self._sym_out
 
     def _sym_sweep(self, mode, plan, tri, rect, zero_first, grid, ws):
@@ -366,6 +377,12 @@ class DirectEngine:
                 with torch.cuda.stream(self.comm_stream):
                     allgather_shards(self.packed, self.layout, self.rank, self.shard_bytes, self.group)
 
+            if p2p and getattr(self, "_p2p_reads_pending", False) and not positions_changed:
+                # two evaluations in a row without a kick_drift (whose barrier orders the ranks): peers may still be
+                # reading this rank's workspace from the previous evaluation
+                self._ws_symm.barrier(channel=3)
+            self._p2p_reads_pending = False
+
             def wait_exchange():
                 if self.world == 1:
                     return
@@ -386,6 +403,20 @@ class DirectEngine:
             else:
                 wait_exchange()
                 self._sym_sweep(mode, plan, True, has_rect, True, grid, ws)
+            if p2p:
+                # fused reduce + finish over peer memory: barrier (every rank's sweeps have completed), then each
+                # owner adds the rows of its shard from all workspaces.  The workspaces are cleared again only after
+                # the next step's first barrier (kick_drift), i.e. after every rank has finished reading.
+                self._ws_symm.barrier(channel=2)
+                if self.n_local > 0:
+                    _lib.check(lib.nb_sym_finish_peers(self.prec, mode, self._ws_peer_ptrs, self.world, self.first,
+                                                       self.n_local, self.G,
+                                                       self.acc.data_ptr() if mode & MODE_FORCE else None,
+                                                       self.phi.data_ptr() if mode & MODE_POT else None,
+                                                       self._stream()))
+                    self.launches += 1
+                self._p2p_reads_pending = True
+                return
             src, first = ws, self.first
             if self.world > 1:
                 reduce_scatter_shards(ws, out, self.layout, self.rank, self.group)   # my shard's sums from every rank

@@ -80,6 +80,19 @@ def check_config(name, pos, mass, h, precision, kernels, rows, tol, rank, world,
         d_eng = max(rel_max(a_loc, acc[sl]) if len(a_loc) else 0.0, rel_max(p_loc, phi[sl]) if len(p_loc) else 0.0)
         sym = eng.symmetric
         del eng
+        d_p2p = 0.0
+        if "--p2p" in sys.argv:
+            # exchange='p2p': workspace in symmetric memory, reduce + finish fused into one kernel over NVLink peer memory
+            eng = DirectEngine(N, mass, h, prec, KERNEL_MAP[kernel], G, EPS2_DEFAULT[precision],
+                               torch.device("cuda", torch.cuda.current_device()), exchange="p2p")
+            eng.load_state(xv)
+            eng.compute(MODE_BOTH, positions_changed=False)
+            eng.compute(MODE_BOTH, positions_changed=False)      # twice: the workspace is cleared and reused
+            torch.cuda.synchronize()
+            a_p, p_p = eng.acc.cpu().numpy(), eng.phi.cpu().numpy()
+            d_p2p = max(rel_max(a_p, acc[sl]) if len(a_p) else 0.0, rel_max(p_p, phi[sl]) if len(p_p) else 0.0)
+            del eng
+            d_eng = max(d_eng, d_p2p)
         if rank == 0:
             errs = []
             for (r0, r1) in blocks:
@@ -93,7 +106,8 @@ def check_config(name, pos, mass, h, precision, kernels, rows, tol, rank, world,
             good = max(errs) <= tol and np.isfinite(acc).all() and np.isfinite(phi).all()
             msgs.append(f"{name} world={world} {precision} {kernel} ({'symmetric' if sym else 'one-sided'} sweep): "
                         f"{'rel-max' if f64 else 'rel-RMS'} vs oracle rows {[f'{e:.2e}' for e in errs]} (tol {tol:g}), "
-                        f"engine vs API rows {d_eng:.1e}, API call {t_api * 1e3:.0f} ms -> {'ok' if good else 'FAIL'}")
+                        f"engine (nccl{' and p2p' if '--p2p' in sys.argv else ''}) vs API rows {d_eng:.1e}, "
+                        f"API call {t_api * 1e3:.0f} ms -> {'ok' if good else 'FAIL'}")
             ok &= bool(good)
         ok &= bool(d_eng <= (1e-12 if f64 else 5e-6))
     return ok
@@ -104,7 +118,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     out = Path(sys.argv[1])
-    which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["c3", "c4", "c5"]
+    which = sys.argv[2].split(",") if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else ["c3", "c4", "c5"]
     oracle.build()
     oracle.set_num_threads(len(os.sched_getaffinity(0)), fast=True)     # torchrun sets OMP_NUM_THREADS=1
     ok, msgs = True, []

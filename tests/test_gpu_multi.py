@@ -35,7 +35,7 @@ def test_baseline_configs_sharded(tmp_path):
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
     worker = Path(__file__).resolve().parent / "mgpu_configs_worker.py"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29537", str(worker), str(tmp_path)]
+           "--master-addr", "127.0.0.1", "--master-port", "29537", str(worker), str(tmp_path), "c3,c4,c5", "--p2p"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=850)
     res = (tmp_path / "result.txt").read_text() if (tmp_path / "result.txt").exists() else ""
     assert r.returncode == 0 and res.startswith("OK"), f"{res}\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}"
