@@ -191,7 +191,7 @@ def gather_rows_padded(padded, layout: ShardLayout, rank: int, group=None, root_
             dist.gather(padded, list(out.split(layout.shard)), dst=root, group=group)
             return out[: layout.N]
         dist.gather(padded, None, dst=root, group=group)
-        return local if local is not None else padded[: layout.count(rank)]
+        return local
     out = torch.empty(shape, dtype=padded.dtype, device=padded.device)
     dist.all_gather_into_tensor(out, padded, group=group)
     return out[: layout.N]
@@ -484,12 +484,25 @@ class DirectEngine:
             # keep operand tensors alive until the kernel has consumed them
             torch.cuda.current_stream(self.device).synchronize()
 
+    def state_device(self, root_only: bool = False):
+        """(N,6) float64 device tensor of the whole system: on every rank, or (root_only) on rank 0 only — the
+        other ranks then get None and send their rows without receiving anything.  No staging copy: the rows are
+        gathered from a persistent shard-sized buffer."""
+        torch = self.torch
+        if self.world == 1:
+            return torch.cat([self.pos, self.vel], dim=1)
+        if getattr(self, "_xv_pad", None) is None:
+            self._xv_pad = torch.zeros((self.layout.shard, 6), dtype=torch.float64, device=self.device)
+        self._xv_pad[: self.n_local, :3] = self.pos
+        self._xv_pad[: self.n_local, 3:] = self.vel
+        full = gather_rows_padded(self._xv_pad, self.layout, self.rank, self.group, root_only=root_only, local=None)
+        if root_only and self.rank != 0:
+            return None
+        return full
+
     def state_numpy(self) -> np.ndarray:
         """(N,6) float64 on the host, identical on all ranks."""
-        torch = self.torch
-        xv_local = torch.cat([self.pos, self.vel], dim=1)
-        full = gather_rows(xv_local, self.layout, self.rank, self.group)
-        return full.cpu().numpy()
+        return self.state_device().cpu().numpy()
 
     # -- force evaluation -----------------------------------------------------
     def compute(self, mode: int = MODE_FORCE, positions_changed: bool = True) -> None:

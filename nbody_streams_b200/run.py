@@ -449,7 +449,7 @@ def run_nbody_gpu(
             def job(xv_np, t=t, step=step, counter=counter):
                 _save_restart(xv_np, t, step, output_path, counter, **_restart_kwargs)
         if async_io:
-            xv_dev = gather_rows(torch.cat([eng.pos, eng.vel], dim=1), eng.layout, eng.rank, eng.group)
+            xv_dev = eng.state_device(root_only=True)     # only the writing rank receives the rows
             if is_root:
                 writer.submit(kind, xv_dev, job)
         else:

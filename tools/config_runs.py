@@ -31,7 +31,7 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-out = [f"# BASELINE configs 4 and 5 as runs on {world} GPU(s) (round 1)\n"]
+out = [f"# BASELINE configs 4 and 5 as runs on {world} GPU(s) (round 2: pair-symmetric sweep)\n"]
 
 steps = arg("--c4-steps", 1000)
 if steps > 0:
