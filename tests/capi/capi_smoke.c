@@ -4,7 +4,8 @@
  *   gcc capi_smoke.c -I../../include -I/usr/local/cuda/include -L<libdir> -lnbody_sm100 -L/usr/local/cuda/lib64 -lcudart -lm
  *
  * Computes Plummer-softened accelerations + potential for N particles in float32_kahan and float64 with
- * nb_direct and checks them against a plain double loop (the reference's CPU algorithm, fields.py:220-256).
+ * nb_direct (one-sided sweep) and nb_direct_sym (pair-symmetric sweep) and checks both against a plain double
+ * loop (the reference's CPU algorithm, fields.py:220-256).
  */
 #include <cuda_runtime_api.h>
 #include <math.h>
@@ -62,20 +63,23 @@ int main(int argc, char** argv) {
 
     int fail = 0;
     const int precs[2] = {NB_PREC_F32_COMP, NB_PREC_F64};
-    for (int p = 0; p < 2; ++p) {
-        const int prec = precs[p];
+    for (int pp = 0; pp < 4; ++pp) {
+        const int prec = precs[pp & 1];
+        const int sym = pp >> 1;                 /* second pass: the pair-symmetric entry points */
         const size_t es = prec == NB_PREC_F64 ? 8 : 4;
         int grid = 0;
-        CHECK_NB(nb_sweep_grid(prec, NB_KERNEL_PLUMMER, NB_MODE_BOTH, &grid));
-        const size_t ws_bytes = nb_workspace_bytes(prec, n, grid, 1);
+        CHECK_NB(sym ? nb_sym_grid(prec, NB_KERNEL_PLUMMER, NB_MODE_BOTH, &grid)
+                     : nb_sweep_grid(prec, NB_KERNEL_PLUMMER, NB_MODE_BOTH, &grid));
+        const size_t ws_bytes = sym ? nb_sym_workspace_bytes(nb_padded_count(n)) : nb_workspace_bytes(prec, n, grid, 1);
         void *packed, *ws, *d_acc, *d_phi;
         CHECK_CUDA(cudaMalloc(&packed, nb_packed_bytes(prec, n)));
         CHECK_CUDA(cudaMalloc(&ws, ws_bytes));
         CHECK_CUDA(cudaMalloc(&d_acc, es * 3 * n));
         CHECK_CUDA(cudaMalloc(&d_phi, es * n));
         /* float64 inputs are cast to the kernel dtype inside nb_pack */
-        CHECK_NB(nb_direct(prec, NB_KERNEL_PLUMMER, NB_MODE_BOTH, d_pos, NB_DT_F64, d_mass, NB_DT_F64, 0.0, d_h, NB_DT_F64, 0.0,
-                           n, G, prec == NB_PREC_F64 ? 1e-30 : 1e-15, packed, ws, ws_bytes, grid, d_acc, d_phi, st));
+        CHECK_NB((sym ? nb_direct_sym : nb_direct)(prec, NB_KERNEL_PLUMMER, NB_MODE_BOTH, d_pos, NB_DT_F64, d_mass, NB_DT_F64, 0.0,
+                                                   d_h, NB_DT_F64, 0.0, n, G, prec == NB_PREC_F64 ? 1e-30 : 1e-15, packed, ws,
+                                                   ws_bytes, grid, d_acc, d_phi, st));
         CHECK_CUDA(cudaStreamSynchronize(st));
         void* acc = malloc(es * 3 * n); void* phi = malloc(es * n);
         CHECK_CUDA(cudaMemcpy(acc, d_acc, es * 3 * n, cudaMemcpyDeviceToHost));
@@ -91,7 +95,7 @@ int main(int argc, char** argv) {
             if (e > pmax) pmax = e;
         }
         const double rms = sqrt(num / den), tol = prec == NB_PREC_F64 ? 1e-12 : 1e-5;
-        printf("prec %d: grid %d, acc rel-RMS %.3e, phi max rel %.3e -> %s\n", prec, grid, rms, pmax, (rms < tol && pmax < 10 * tol) ? "ok" : "FAIL");
+        printf("prec %d %s: grid %d, acc rel-RMS %.3e, phi max rel %.3e -> %s\n", prec, sym ? "symmetric" : "one-sided", grid, rms, pmax, (rms < tol && pmax < 10 * tol) ? "ok" : "FAIL");
         if (!(rms < tol && pmax < 10 * tol)) fail = 1;
         /* invalid arguments are reported, not crashed on */
         if (nb_direct(prec, 9, NB_MODE_BOTH, d_pos, NB_DT_F64, d_mass, NB_DT_F64, 0.0, d_h, NB_DT_F64, 0.0, n, G, 1e-15, packed, ws, ws_bytes, grid, d_acc, d_phi, st) != NB_E_INVALID_ARG) fail = 1;

@@ -100,3 +100,46 @@ def test_kick_drift_pack_and_energy_stay_inside_their_buffers(prec):
     torch.cuda.synchronize()
     for name, g in (("pos", pos), ("vel", vel), ("packed", packed), ("energy partials", part), ("energy out", out)):
         assert g.intact(), f"write outside the {name} buffer"
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_F32, _lib.PREC_F32_COMP, _lib.PREC_F64])
+@pytest.mark.parametrize("kernel_id", [1, 4])
+@pytest.mark.parametrize("n", [1, 257, 5000, 70001])
+def test_nb_direct_sym_stays_inside_its_buffers(prec, kernel_id, n):
+    """Same for the pair-symmetric path: its atomics go to 4 doubles per padded slot of the workspace and nowhere
+    else (per-particle masses / softening: general tiles; the last block is partial and padded)."""
+    import torch
+
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(n)
+    es = 8 if prec == _lib.PREC_F64 else 4
+    tdt = torch.float64 if es == 8 else torch.float32
+    pos = torch.from_numpy(rng.standard_normal((n, 3))).to(dev)
+    mass = torch.from_numpy(rng.uniform(0.5, 2.0, n)).to(dev)
+    h = torch.from_numpy(rng.uniform(0.01, 0.1, n)).to(dev)
+    grid = C.c_int(0)
+    _lib.check(lib.nb_sym_grid(prec, kernel_id, _lib.MODE_BOTH, C.byref(grid)))
+    ws_bytes = lib.nb_sym_workspace_bytes(lib.nb_padded_count(n))
+    assert ws_bytes == 32 * lib.nb_padded_count(n)
+    packed = Guarded(lib.nb_packed_bytes(prec, n), dev)
+    ws = Guarded(ws_bytes, dev)
+    acc = Guarded(es * 3 * n, dev)
+    phi = Guarded(es * n, dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.nb_direct_sym(prec, kernel_id, _lib.MODE_BOTH, pos.data_ptr(), _lib.DT_F64, mass.data_ptr(),
+                                 _lib.DT_F64, 0.0, h.data_ptr(), _lib.DT_F64, 0.0, n, 1.0, 1e-15, packed.ptr, ws.ptr,
+                                 ws_bytes, grid.value, acc.ptr, phi.ptr, stream))
+    torch.cuda.synchronize()
+    for name, g in (("packed", packed), ("workspace", ws), ("acc", acc), ("phi", phi)):
+        assert g.intact(), f"write outside the {name} buffer"
+    a = acc.payload(tdt, (n, 3))
+    p = phi.payload(tdt, (n,))
+    assert torch.isfinite(a).all() and torch.isfinite(p).all()
+    if n > 1:
+        assert (p < 0).all()
+    # a too small workspace is refused, not overrun
+    rc = lib.nb_direct_sym(prec, kernel_id, _lib.MODE_BOTH, pos.data_ptr(), _lib.DT_F64, mass.data_ptr(), _lib.DT_F64, 0.0,
+                           h.data_ptr(), _lib.DT_F64, 0.0, n, 1.0, 1e-15, packed.ptr, ws.ptr, ws_bytes - 32, grid.value,
+                           acc.ptr, phi.ptr, stream)
+    assert rc == -2      # NB_E_WORKSPACE
