@@ -120,8 +120,11 @@ class ClockSampler:
 
 def config_dict(args, N) -> dict:
     """Identical for both arms (the driver compares the dicts)."""
+    tag = "BASELINE config 3" if (N == 1_000_000 and args.precision == "float32_kahan") else (
+        "BASELINE config 4 size" if (N == 262_144 and args.precision == "float64") else "non-default workload")
     return {"workload": f"Plummer N={N} direct {args.precision} force+potential, kernel={args.kernel}, "
-                        f"softening={args.softening} (BASELINE config 3)"}
+                        f"softening={args.softening} ({tag})",
+            "l2": "GPU arm: 256 MiB memset between steps (inside the timed region); CPU arm: not applicable"}
 
 
 def workload(args):
@@ -138,8 +141,9 @@ def cpu_sample(args, xv, m, seconds: float) -> dict:
     oracle.build()
     oracle.set_num_threads(len(os.sched_getaffinity(0)), fast=True)   # all host cores (torchrun sets OMP_NUM_THREADS=1)
     N = xv.shape[0]
-    pos = xv[:, :3].astype(np.float32)
-    kw = dict(kernel=args.kernel, precision="float32", fast=True)
+    f64 = args.precision == "float64"
+    pos = xv[:, :3] if f64 else xv[:, :3].astype(np.float32)
+    kw = dict(kernel=args.kernel, precision="float64" if f64 else "float32", fast=True)
 
     def run(rows):
         t0 = time.perf_counter()
@@ -161,7 +165,8 @@ def cpu_sample(args, xv, m, seconds: float) -> dict:
             break
     return {"value": rows * N / t, "unit": "interactions/s", "cores": oracle.num_threads(True), "kind": "port",
             "sample": f"rows [0,{rows}) of the N={N} Plummer workload against all N, force pass + potential pass "
-                      f"({args.kernel}, float32 pair math / float64 sums as the reference CPU path), {t:.1f} s",
+                      f"({args.kernel}, " + ("float64" if f64 else "float32 pair math / float64 sums") +
+                      f" as the reference CPU path), {t:.1f} s",
             "seconds": t, "rows": rows}
 
 
@@ -181,7 +186,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "pairwise interactions/s", "value": val, "unit": "interactions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": N * N / val * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if args.precision == "float64" else "f32", "data": "synthetic",
         "config": config_dict(args, N),
         "details": {"note": "reference CPU algorithm (C/OpenMP port of the Numba path; the reference is Python and "
                             "cannot travel to the GPU box); ms_per_step extrapolates the sampled rate to N^2"},
@@ -482,7 +488,6 @@ def main():
                                + ("pushed to all ranks by the fused kick+drift kernel over NVLink peer memory"
                                   if (world > 1 and args.exchange == "p2p") else "all-gathered over NCCL")
                                + (", local-shard sweep overlapped with the gather" if world > 1 and not args.no_overlap else ""),
-                "l2": "256 MiB memset between steps (inside the timed region)",
                 "tuning_variant": int(lib.nb_get_variant(prec)),
             },
             "fraction_of_fp32_peak": value * FLOPS_PER_INTERACTION / 1e12 / (peak_tf * world),

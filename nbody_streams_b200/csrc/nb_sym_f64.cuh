@@ -21,7 +21,7 @@ constexpr int SYM_STAGES_F64 = 2;                       // a tile takes ~40k cyc
 #ifndef NB_SYM_UNROLL_F64
 #define NB_SYM_UNROLL_F64 2
 #endif
-constexpr int SYM_UNROLL_F64 = NB_SYM_UNROLL_F64;       // rotation steps per loop iteration (non-spline kernels)
+constexpr int SYM_UNROLL_F64 = NB_SYM_UNROLL_F64;       // rotation steps per loop iteration
 
 __device__ __forceinline__ double shfl_d(const double v, const int src) {
     int lo = __double2loint(v), hi = __double2hiint(v);
@@ -130,7 +130,7 @@ __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ s
     const double* __restrict__ sM = reinterpret_cast<const double*>(stage) + COMP_M * TJ;
     const double* __restrict__ sC = reinterpret_cast<const double*>(stage) + COMP_C * TJ;
     constexpr bool kUsesC = (KID == NB_KERNEL_PLUMMER || KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
-    constexpr int kUnroll = (KID == 4 /* spline: the exact step's state copy */) ? 1 : SYM_UNROLL_F64;
+    constexpr int kUnroll = SYM_UNROLL_F64;   // also for the spline (measured: +3 % force+potential, +7 % potential)
     const int src = (lane + 1) & 31;
 
 #pragma unroll 1
