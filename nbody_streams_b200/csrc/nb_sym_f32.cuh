@@ -140,27 +140,6 @@ __device__ __forceinline__ void sym_cold_to_hot(const IState<NP>& S, SymHot32<NP
     }
 }
 
-// the whole step (NP i-pairs x this lane's j) with the exact spline; U: unweighted sums
-template <int MODE, bool U, int NP>
-__device__ __noinline__ void sym_spline_exact_step(SymCold32<NP>* T, const float xj, const float yj, const float zj,
-                                                   const float mj_in, const float cj, const float eps2) {
-    float jx0, jx1, jy0, jy1, jz0, jz1, jp0, jp1;
-    upk(T->J.x, jx0, jx1); upk(T->J.y, jy0, jy1); upk(T->J.z, jz0, jz1); upk(T->J.p, jp0, jp1);
-    const float mj = U ? 1.f : mj_in;
-#pragma unroll
-    for (int q = 0; q < NP; ++q) {
-        float x0, x1, y0, y1, z0, z1, m0, m1, ax0, ax1, ay0, ay1, az0, az1, sp0, sp1;
-        upk(T->S.x[q], x0, x1); upk(T->S.y[q], y0, y1); upk(T->S.z[q], z0, z1);
-        upk(T->S.ax[q], ax0, ax1); upk(T->S.ay[q], ay0, ay1); upk(T->S.az[q], az0, az1); upk(T->S.sp[q], sp0, sp1);
-        upk(T->m[q], m0, m1);
-        if (U) m0 = m1 = 1.f;
-        sym_spline_exact<MODE>(xj, yj, zj, mj, cj, x0, y0, z0, m0, T->S.c0[q], ax0, ay0, az0, sp0, jx0, jy0, jz0, jp0, eps2);
-        sym_spline_exact<MODE>(xj, yj, zj, mj, cj, x1, y1, z1, m1, T->S.c1[q], ax1, ay1, az1, sp1, jx1, jy1, jz1, jp1, eps2);
-        T->S.ax[q] = pk(ax0, ax1); T->S.ay[q] = pk(ay0, ay1); T->S.az[q] = pk(az0, az1); T->S.sp[q] = pk(sp0, sp1);
-    }
-    T->J.x = pk(jx0, jx1); T->J.y = pk(jy0, jy1); T->J.z = pk(jz0, jz1); T->J.p = pk(jp0, jp1);
-}
-
 // ---------------------------------------------------------------------------
 // one symmetric j-tile against this thread's NP pairs; jw = this warp's slice [4][TJ] of the j-side buffer.
 //   ST = SymHot32 (U: uniform fast path) or IState (general path; ci0/ci1/mi = per-particle terms)
@@ -318,8 +297,7 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
 // the separations and r^2 of its NP pairs and their minimum (one FMNMX3 per packed pair); the spline is
 // exactly Newtonian for r >= h (cuda_kernels.py:64-67), so unless that minimum lies below the largest
 // softening term that can apply the step finishes on the branch-free Newtonian path; otherwise (rare) the
-// whole step is redone by sym_spline_exact_step with the reference's piecewise polynomial.  The exact path
-// works on a copy of the thread state, which costs registers when several steps are in flight: measured best
+// whole step is redone in place with the reference's piecewise polynomial (sym_spline_exact).  Measured best
 // with one step per iteration and the three phases in program order (round-2 experiments, N = 262144 force:
 // this loop 21.4 ms; the software-pipelined loop with the exact step moved out of line through workspace atomics
 // 23.3-24.8 ms at 1, 2 or 4 steps per iteration; this loop with that out-of-line step 24.8 ms).
@@ -374,22 +352,25 @@ __device__ __forceinline__ void sym_tile_f32_spline(const unsigned char* __restr
                 dmin = fminf(dmin, fminf(d0, d1));
             }
             if (dmin < (U ? c_pair : fmaxf(cj, cmax_i))) {
-                SymCold32<NP> T;
+                // exact step, in place: every pair of the step with the reference's piecewise polynomial.  (Moving
+                // this behind a call on a state copy was tried first: 8 % slower at h/a = 0.01 and 2-4x slower once a few
+                // percent of the steps take this path, h/a >= 0.2 — profiles/r02_spline_rate_vs_softening.md.)
+                float jx0, jx1, jy0, jy1, jz0, jz1, jp0, jp1;
+                upk(J.x, jx0, jx1); upk(J.y, jy0, jy1); upk(J.z, jz0, jz1); upk(J.p, jp0, jp1);
+                const float mje = U ? 1.f : mj;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
-                    T.S.x[q] = S.x[q]; T.S.y[q] = S.y[q]; T.S.z[q] = S.z[q];
-                    T.S.ax[q] = S.ax[q]; T.S.ay[q] = S.ay[q]; T.S.az[q] = S.az[q]; T.S.sp[q] = S.sp[q];
-                    T.S.c0[q] = U ? c_pair : ci0[q];
-                    T.S.c1[q] = U ? c_pair : ci1[q];
-                    T.m[q]    = U ? 0ull : mi[q];
+                    float x0, x1, y0, y1, z0, z1, m0 = 1.f, m1 = 1.f, ax0, ax1, ay0, ay1, az0, az1, sp0, sp1;
+                    upk(S.x[q], x0, x1); upk(S.y[q], y0, y1); upk(S.z[q], z0, z1);
+                    upk(S.ax[q], ax0, ax1); upk(S.ay[q], ay0, ay1); upk(S.az[q], az0, az1); upk(S.sp[q], sp0, sp1);
+                    if (!U) upk(mi[q], m0, m1);
+                    sym_spline_exact<MODE>(xj, yj, zj, mje, cj, x0, y0, z0, m0, U ? c_pair : ci0[q], ax0, ay0, az0, sp0,
+                                           jx0, jy0, jz0, jp0, eps2);
+                    sym_spline_exact<MODE>(xj, yj, zj, mje, cj, x1, y1, z1, m1, U ? c_pair : ci1[q], ax1, ay1, az1, sp1,
+                                           jx1, jy1, jz1, jp1, eps2);
+                    S.ax[q] = pk(ax0, ax1); S.ay[q] = pk(ay0, ay1); S.az[q] = pk(az0, az1); S.sp[q] = pk(sp0, sp1);
                 }
-                T.J = J;
-                sym_spline_exact_step<MODE, U, NP>(&T, xj, yj, zj, mj, cj, eps2);
-#pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    S.ax[q] = T.S.ax[q]; S.ay[q] = T.S.ay[q]; S.az[q] = T.S.az[q]; S.sp[q] = T.S.sp[q];
-                }
-                J = T.J;
+                J.x = pk(jx0, jx1); J.y = pk(jy0, jy1); J.z = pk(jz0, jz1); J.p = pk(jp0, jp1);
             } else {
                 f2 rinv[NP];
 #pragma unroll

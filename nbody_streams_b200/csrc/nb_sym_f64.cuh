@@ -94,31 +94,6 @@ struct SymCold64 {
     JAcc64 J;
 };
 
-// the whole step (NI i x this lane's j) with the exact cubic spline (reference cuda_kernels.py:687-752,
-// :1228-1297 restated in spline_inside); U: unweighted sums
-template <int MODE, bool U, int NI>
-__device__ __noinline__ void sym_spline_exact_step_f64(SymCold64<NI>* T, const double xj, const double yj,
-                                                       const double zj, const double mj_in, const double cj,
-                                                       const double eps2) {
-    const double mj = U ? 1.0 : mj_in;
-#pragma unroll
-    for (int q = 0; q < NI; ++q) {
-        const double dx = xj - T->S.x[q], dy = yj - T->S.y[q], dz = zj - T->S.z[q];
-        const double d  = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
-        const double h2 = fmax(cj, T->S.c[q]);
-        const double ri = rsqrt_f64(d);
-        double w, p;
-        if (d < h2) {
-            spline_inside<double>(d, ri, rsqrt_f64(h2), w, p);
-        } else {
-            p = ri;
-            w = ri * (ri * ri);
-        }
-        sym_apply_f64<MODE, false>(w, p, dx, dy, dz, mj, U ? 1.0 : T->m[q], T->S.ax[q], T->S.ay[q], T->S.az[q],
-                                   T->S.sp[q], T->J);
-    }
-}
-
 // one symmetric j-tile; jw = this warp's slice [4][TJ] of the j-side buffer
 template <int KID, int MODE, bool U, int NI>
 __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ stage, IState64<NI>& S,
@@ -178,14 +153,21 @@ __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ s
                 }
                 const double h2lim = U ? c_pair : fmax(cj, cmax_i);
                 if (hi_min <= __double2hiint(h2lim)) {
-                    SymCold64<NI> T;
-                    T.S = S;
+                    // exact step, in place: every pair of the step with the reference's piecewise polynomial
+                    // (cuda_kernels.py:687-752, :1228-1297 restated in spline_inside)
 #pragma unroll
-                    for (int q = 0; q < NI; ++q) T.m[q] = mi[q];
-                    T.J = J;
-                    sym_spline_exact_step_f64<MODE, U, NI>(&T, xj, yj, zj, mj, cj, eps2);
-                    S = T.S;
-                    J = T.J;
+                    for (int q = 0; q < NI; ++q) {
+                        const double h2 = U ? c_pair : fmax(cj, S.c[q]);
+                        const double ri = rsqrt_f64(d[q]);
+                        double w, p;
+                        if (d[q] < h2) {
+                            spline_inside<double>(d[q], ri, rsqrt_f64(h2), w, p);
+                        } else {
+                            p = ri;
+                            w = ri * (ri * ri);
+                        }
+                        sym_apply_f64<MODE, U>(w, p, dx[q], dy[q], dz[q], mj, mi[q], S.ax[q], S.ay[q], S.az[q], S.sp[q], J);
+                    }
                 } else {
 #pragma unroll
                     for (int q = 0; q < NI; ++q) {
