@@ -33,6 +33,10 @@ constexpr int SYM_FLUSH_TILES = 8;                       // i-side: float runnin
 #define NB_SYM_UNROLL 8
 #endif
 constexpr int SYM_UNROLL = NB_SYM_UNROLL;                 // steps per iteration of the hot loop
+// The spline's force and force+potential sweeps use their own non-pipelined loop (sym_tile_f32_spline: 19.75 / 22.9 ms at
+// N = 262144 against 21.8-22.4 / 22.9-23.8 ms in the pipelined loop at 1, 2 or 4 steps per iteration); only its
+// potential-only sweep is faster pipelined (12.25 against 13.7 ms, 4 steps per iteration).
+constexpr int SYM_UNROLL_SPLINE = 4;
 
 __device__ __forceinline__ f2 shfl2(const f2 v, const int src) {
     float lo, hi;
@@ -179,10 +183,11 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
             mn = sM[j1]; cn = sC[j1];
         }
     }
-    static_assert(KID != NB_KERNEL_SPLINE, "the spline has its own, non-pipelined loop: sym_tile_f32_spline");
     f2 dx[NP], dy[NP], dz[NP], rinv[NP], h2[NP];
+    bool exact = false;
     // separations, softening term, r^2 and reciprocal square roots of the step whose record is (xj.., cj)
     auto prepare = [&]() {
+        float dmin = 3.0e38f;
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             dx[q] = sub2(splat(xj), S.x[q]);
@@ -198,16 +203,37 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
             const f2 d = fma2(dx[q], dx[q], fma2(dy[q], dy[q], fma2(dz[q], dz[q], c)));
             float d0, d1;
             upk(d, d0, d1);
+            if (KID == NB_KERNEL_SPLINE) dmin = fminf(dmin, fminf(d0, d1));
             rinv[q] = pk(rsqrt_approx(d0), rsqrt_approx(d1));
         }
+        if (KID == NB_KERNEL_SPLINE) exact = dmin < (U ? c_pair : fmaxf(cj, cmax_i));
     };
     prepare();
 
     JAcc32 J;
     J.x = J.y = J.z = J.p = 0ull;
-#pragma unroll SYM_UNROLL
+    constexpr int kUnroll = (KID == NB_KERNEL_SPLINE) ? SYM_UNROLL_SPLINE : SYM_UNROLL;
+#pragma unroll kUnroll
     for (int t = 0; t < TJ; ++t) {
-        {
+        if (KID == NB_KERNEL_SPLINE && exact) {
+            // exact step, in place (see sym_tile_f32_spline)
+            float jx0, jx1, jy0, jy1, jz0, jz1, jp0, jp1;
+            upk(J.x, jx0, jx1); upk(J.y, jy0, jy1); upk(J.z, jz0, jz1); upk(J.p, jp0, jp1);
+            const float mje = U ? 1.f : mj;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                float x0, x1, y0, y1, z0, z1, m0 = 1.f, m1 = 1.f, ax0, ax1, ay0, ay1, az0, az1, sp0, sp1;
+                upk(S.x[q], x0, x1); upk(S.y[q], y0, y1); upk(S.z[q], z0, z1);
+                upk(S.ax[q], ax0, ax1); upk(S.ay[q], ay0, ay1); upk(S.az[q], az0, az1); upk(S.sp[q], sp0, sp1);
+                if (!U) upk(mi[q], m0, m1);
+                sym_spline_exact<MODE>(xj, yj, zj, mje, cj, x0, y0, z0, m0, U ? c_pair : ci0[q], ax0, ay0, az0, sp0,
+                                       jx0, jy0, jz0, jp0, eps2);
+                sym_spline_exact<MODE>(xj, yj, zj, mje, cj, x1, y1, z1, m1, U ? c_pair : ci1[q], ax1, ay1, az1, sp1,
+                                       jx1, jy1, jz1, jp1, eps2);
+                S.ax[q] = pk(ax0, ax1); S.ay[q] = pk(ay0, ay1); S.az[q] = pk(az0, az1); S.sp[q] = pk(sp0, sp1);
+            }
+            J.x = pk(jx0, jx1); J.y = pk(jy0, jy1); J.z = pk(jz0, jz1); J.p = pk(jp0, jp1);
+        } else {
             // kernel factors (mass-less: w ~ 1/r^3, p ~ 1/r) applied to both sides
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
@@ -299,8 +325,9 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
 // softening term that can apply the step finishes on the branch-free Newtonian path; otherwise (rare) the
 // whole step is redone in place with the reference's piecewise polynomial (sym_spline_exact).  Measured best
 // with one step per iteration and the three phases in program order (round-2 experiments, N = 262144 force:
-// this loop 21.4 ms; the software-pipelined loop with the exact step moved out of line through workspace atomics
-// 23.3-24.8 ms at 1, 2 or 4 steps per iteration; this loop with that out-of-line step 24.8 ms).
+// this loop with the exact step in place 19.75 ms; with the exact step behind a call on a state copy 21.4 ms;
+// with the exact step moved out of line through workspace atomics 24.8 ms; the software-pipelined loop
+// 21.8-22.4 ms with the in-place step, 23.3-24.8 ms with the out-of-line ones).
 // ---------------------------------------------------------------------------
 template <int MODE, bool U, int NP, typename ST>
 __device__ __forceinline__ void sym_tile_f32_spline(const unsigned char* __restrict__ stage, ST& S, const f2* mi,
@@ -435,7 +462,7 @@ __device__ __forceinline__ void sym_tile_f32_any(const unsigned char* __restrict
                                                  const float* ci0, const float* ci1, const float cmax_i,
                                                  const float c_pair, const float eps2, float* __restrict__ jw,
                                                  const int lane) {
-    if constexpr (KID == NB_KERNEL_SPLINE)
+    if constexpr (KID == NB_KERNEL_SPLINE && MODE != NB_MODE_POT)
         sym_tile_f32_spline<MODE, U, NP, ST>(stage, S, mi, ci0, ci1, cmax_i, c_pair, eps2, jw, lane);
     else
         sym_tile_f32<KID, MODE, U, NP, ST>(stage, S, mi, ci0, ci1, cmax_i, c_pair, eps2, jw, lane);
