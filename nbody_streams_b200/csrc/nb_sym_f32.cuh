@@ -341,6 +341,8 @@ __device__ __forceinline__ void sym_tile_f32_spline(const unsigned char* __restr
     const float* __restrict__ sC = reinterpret_cast<const float*>(stage) + COMP_C * TJ;
     const f2 ceps = splat(eps2);
     const int src = (lane + 1) & 31;
+    // steps per loop iteration: measured at N = 262144 — force 19.8 ms (1 step) / 21.1 ms (2); force+potential 22.9 / 22.0
+    constexpr int kSteps = (MODE == NB_MODE_BOTH) ? 2 : 1;
 
 #pragma unroll 1
     for (int rho = 0; rho < TJ / 32; ++rho) {
@@ -353,7 +355,7 @@ __device__ __forceinline__ void sym_tile_f32_spline(const unsigned char* __restr
             mn = sM[jb + lane];
             cn = sC[jb + lane];
         }
-#pragma unroll 1
+#pragma unroll kSteps
         for (int s = 0; s < 32; ++s) {
             const float xj = xn, yj = yn, zj = zn, mj = mn, cj = cn;
             {
