@@ -314,6 +314,10 @@ def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, m
     if N == 0:
         return acc, phi
     sym = n_sources is None and use_symmetric(N, algorithm)
+    # sources restricted to the first n_sources particles on ONE rank: still pair-symmetric — the pairs inside the
+    # source set once (triangle over the source tiles), and (test-particle tiles) x (source tiles) as a rectangle whose
+    # j-side contributions vanish with the test particles' zero masses
+    sym_sources = n_sources is not None and world == 1 and use_symmetric(N, algorithm)
     with torch.cuda.device(device):
         grid = _grid_for(prec, kernel_id, mode, device, sym=sym)
         n_slots = layout.n_slots if world > 1 else lib.nb_padded_count(N)
@@ -329,6 +333,26 @@ def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, m
             _lib.check(lib.nb_direct_sym(prec, kernel_id, mode, pos_t.data_ptr(), _dt_code(pos_t), mass_ptr, mass_dt,
                                          float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, float(G), float(eps2),
                                          packed.data_ptr(), ws.data_ptr(), ws_bytes, grid, acc_ptr, phi_ptr, stream))
+        elif sym_sources:
+            grid = _grid_for(prec, kernel_id, mode, device, sym=True)
+            tile = lib.nb_tile_j()
+            n_src = max(0, min(int(n_sources), N))
+            t_src, t_all = lib.nb_padded_count(n_src) // tile, n_slots // tile      # source tiles, all tiles
+            ws_bytes = lib.nb_sym_workspace_bytes(n_slots)
+            ws = _scratch(device, "workspace", ws_bytes)
+            _lib.check(lib.nb_pack(prec, kernel_id, packed.data_ptr(), 0, pos_t.data_ptr(), _dt_code(pos_t),
+                                   mass_ptr, mass_dt, float(mass_scalar), h_ptr, h_dt, float(h_scalar), N, n_slots,
+                                   float(eps2), stream))
+            args = (float(eps2), ws.data_ptr(), ws_bytes, n_slots)
+            if t_src > 0:       # pairs inside the source tiles (the straddling tile carries zero-mass test particles)
+                _lib.check(lib.nb_sym_sweep(prec, kernel_id, mode, packed.data_ptr(), N, 0, t_src, 1, 0, 0, 0, 0, 0, 0,
+                                            0, 0, *args, 1, grid, stream))
+            else:
+                ws[:ws_bytes].zero_()
+            if t_all > t_src and t_src > 0:   # remaining (test-particle) tiles against the source tiles
+                _lib.check(lib.nb_sym_sweep(prec, kernel_id, mode, packed.data_ptr(), N, t_src, t_all, 0, 0, t_src, 0, 0,
+                                            0, 0, 0, 0, *args, 0, grid, stream))
+            _lib.check(lib.nb_sym_finish(prec, mode, ws.data_ptr(), 0, N, float(G), acc_ptr, phi_ptr, stream))
         elif world == 1 and n_sources is None:
             ws_bytes = lib.nb_workspace_bytes(prec, N, grid, 1)
             ws = _scratch(device, "workspace", ws_bytes)

@@ -174,3 +174,28 @@ def test_auto_selection_threshold(nb):
     assert use_symmetric(10, "symmetric") and not use_symmetric(10**7, "onesided")
     with pytest.raises(ValueError):
         use_symmetric(10, "both")
+
+
+@pytest.mark.parametrize("precision", ["float64", "float32_kahan"])
+def test_n_sources_takes_the_symmetric_path_too(nb, precision):
+    """Sources restricted to the first n_sources particles (unbinding): triangle over the source tiles + rectangle of
+    the test-particle tiles, against the oracle with the test particles' masses zeroed and against the one-sided sweep."""
+    n, n_src = 40_000, 25_001                     # n_src inside a tile
+    xv, m = nb.make_plummer_sphere(n, M_total=1e9, a=1.0, seed=21)
+    pos = xv[:, :3]
+    kw = dict(precision=precision, kernel="spline", n_sources=n_src)
+    a_s, p_s = nb.compute_nbody_forces_potential_gpu(pos, m, 0.03, G, algorithm="symmetric", **kw)
+    a_o, p_o = nb.compute_nbody_forces_potential_gpu(pos, m, 0.03, G, algorithm="onesided", **kw)
+    m0 = m.copy()
+    m0[n_src:] = 0.0
+    for rows in ((0, 700), (24_700, 25_400), (39_300, 40_000)):      # sources, the straddling tile, test particles
+        ref, pref = _oracle(pos, m0, np.full(n, 0.03), "spline", precision, rows=rows, fast=True)
+        _check(a_s[rows[0]:rows[1]], p_s[rows[0]:rows[1]], ref, pref, precision)
+    if precision == "float64":
+        assert rel_max(a_s, a_o) <= 1e-12 and rel_max(p_s, p_o) <= 1e-12
+    else:
+        assert rel_rms(a_s, a_o) <= 2e-6 and rel_rms(p_s, p_o) <= 2e-6
+    # n_sources = 0: nothing gravitates
+    a0, p0 = nb.compute_nbody_forces_potential_gpu(pos, m, 0.03, G, precision=precision, kernel="spline", n_sources=0,
+                                                   algorithm="symmetric")
+    assert np.all(a0 == 0) and np.all(p0 == 0)

@@ -135,3 +135,15 @@ def test_n_sources_scalar_mass_forces_and_validation():
     np.testing.assert_allclose(phi, oracle.compute_nbody_potential_cpu(pos, m0, 0.05, kernel="plummer"), rtol=1e-12)
     with pytest.raises(ValueError, match="n_sources"):
         compute_nbody_potential_gpu(pos, 2.0, 0.05, n_sources=2001)
+
+
+def test_unbinding_above_the_symmetric_threshold_against_the_oracle():
+    """N = 40k: the potential sweeps run the pair-symmetric kernels (sources = bound particles)."""
+    xv, m = _stripped_satellite(40_000, 11)
+    (ref,), cpr, cvr = oracle.iterative_unbinding_cpu(xv[:, :3], xv[:, 3:], m, softening=0.02, kernel="spline")
+    (bd,), cp, cv = iterative_unbinding(xv[:, :3], xv[:, 3:], m, potential_compute_method="direct_gpu", softening=0.02,
+                                        verbose=False, precision="float64", kernel="spline")
+    assert 0.5 * len(ref) < ref.sum() < 0.9 * len(ref)
+    assert (bd != ref).sum() <= 1          # double atomics: a particle with |E| within 1e-15 |phi| of 0 may flip
+    np.testing.assert_allclose(cp, cpr, rtol=1e-10)
+    np.testing.assert_allclose(cv, cvr, rtol=1e-10)
