@@ -263,7 +263,10 @@ def _to_host(t):
         # therefore pins three blocks and hands two straight back to torch's caching host allocator: later calls
         # find a cached block as long as no more than two earlier results of that size are alive.
         key = (t.dtype, tuple(t.shape))
-        if key not in _PINNED_SIZES_SEEN:
+        nbytes = t.numel() * t.element_size()
+        # (bounded: results between 1 MB and 256 MB, at most 8 distinct shapes per process — torch's host allocator
+        # never returns pinned blocks to the OS)
+        if key not in _PINNED_SIZES_SEEN and (1 << 20) <= nbytes <= (256 << 20) and len(_PINNED_SIZES_SEEN) < 8:
             _PINNED_SIZES_SEEN.add(key)
             spare = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for _ in range(2)]
             del spare
