@@ -8,7 +8,10 @@ namespace nb {
 
 enum { SYM_OP_LAUNCH = 0, SYM_OP_QUERY = 1 };
 
-constexpr int SYM_MINB_F32 = 4;   // resident CTAs / SM the f32 kernel is compiled for (<= 128 registers)
+#ifndef NB_SYM_MINB_F32
+#define NB_SYM_MINB_F32 4
+#endif
+constexpr int SYM_MINB_F32 = NB_SYM_MINB_F32;   // resident CTAs / SM the f32 kernel is compiled for (4: <= 128 registers)
 constexpr int SYM_MINB_F64 = 3;
 
 // cudaFuncSetAttribute is needed once per (kernel, device), not per launch

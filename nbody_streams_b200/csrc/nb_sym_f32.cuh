@@ -25,7 +25,10 @@
 
 namespace nb {
 
-constexpr int SYM_NP          = 4;                       // packed i-pairs per thread
+#ifndef NB_SYM_NP
+#define NB_SYM_NP 4
+#endif
+constexpr int SYM_NP          = NB_SYM_NP;               // packed i-pairs per thread
 constexpr int SYM_IB_F32      = THREADS * 2 * SYM_NP;    // 1024 i-particles per CTA
 constexpr int SYM_TPB_F32     = SYM_IB_F32 / TJ;         // 4 tiles per i-block
 constexpr int SYM_FLUSH_TILES = 8;                       // i-side: float running sums -> double workspace
