@@ -169,9 +169,10 @@ int nb_direct(int prec, int kernel_id, int mode,
  * double additions only (not bitwise; use nb_sweep for bitwise reproducibility).
  * NB_PREC_F32 and NB_PREC_F32_COMP share one implementation here (float pair
  * arithmetic, <= 256-term float partial sums, double above).
+ * With fewer than 4 units per CTA a tile is swept in 2 or 4 parts, one unit each.
  * nb_sym_min_n(): particle count from which callers should prefer this path
- * (env NB_SYM_MIN_N, default 32768; below it the one-sided sweep's finer work
- * units fill the GPU better). */
+ * (env NB_SYM_MIN_N, default 8192: measured crossover on one B200; below it the
+ * one-sided sweep's finer work units fill the GPU better). */
 long   nb_sym_min_n(void);
 int    nb_set_sym_min_n(long n);
 int    nb_sym_block_tiles(int prec);

@@ -121,7 +121,7 @@ int dispatch_sym(int prec, int kid, int mode, int op, const SymArgs* a, int grid
 }
 int sym_tpb(int prec) { return prec == NB_PREC_F64 ? SYM_TPB_F64 : SYM_TPB_F32; }
 
-constexpr long SYM_MIN_N_DEFAULT = 32768;   // below this the one-sided sweep's finer work units win
+constexpr long SYM_MIN_N_DEFAULT = 8192;   // below this the one-sided sweep's finer work units win (r02_n_sweep.md)
 long g_sym_min_n = -1;
 
 struct SlotLayout {
@@ -373,6 +373,7 @@ int nb_sym_sweep(int prec, int kernel_id, int mode, const void* packed, long n_j
     a.nT   = it_end - it_begin;
     a.n_ib = (a.nT + TPB - 1) / TPB;
     a.tri  = tri ? 1 : 0;
+    a.split_log2 = 0;
     a.rA0 = ra_begin; a.lenA = ra_end - ra_begin;
     a.rB0 = rb_begin; a.lenB = rb_end - rb_begin;
     a.rC0 = rc_begin; a.lenC = rc_end - rc_begin;
@@ -382,8 +383,10 @@ int nb_sym_sweep(int prec, int kernel_id, int mode, const void* packed, long n_j
     a.eps2 = eps2;
     a.ws   = static_cast<double*>(workspace);
     if (a.n_ib == 0) return 0;
-    a.total = prec == NB_PREC_F64 ? sym_prefix<SYM_TPB_F64>(a, a.n_ib) : sym_prefix<SYM_TPB_F32>(a, a.n_ib);
-    if (a.total <= 0) return 0;
+    const long long tile_units = prec == NB_PREC_F64 ? sym_prefix<SYM_TPB_F64>(a, a.n_ib) : sym_prefix<SYM_TPB_F32>(a, a.n_ib);
+    if (tile_units <= 0) return 0;
+    a.split_log2 = sym_pick_split_log2(tile_units, grid);
+    a.total      = tile_units << a.split_log2;
     return dispatch_sym(prec, kernel_id, mode, SYM_OP_LAUNCH, &a, grid, nullptr, st);
 }
 

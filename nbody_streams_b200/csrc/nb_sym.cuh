@@ -28,7 +28,9 @@ struct SymArgs {
     int tri;                      // sweep the triangle inside the i-range
     int rA0, lenA, rB0, lenB;     // rectangle j-tile ranges (every i-block)
     int rC0, lenC, ibC0, ibC1;    // extra range for i-blocks [ibC0, ibC1)
-    long long total;              // work units
+    int split_log2;               // a tile is swept in 2^split_log2 parts, one work unit each (small problems: more
+                                  // units than CTAs); unit indices below are in these SUB-units
+    long long total;              // work units (sub-units)
     double eps2;
     double* ws;                   // [slots][4] doubles: sum of ax, ay, az, s_phi (atomically accumulated)
 };
@@ -90,6 +92,14 @@ __host__ __device__ inline int sym_tile(const SymArgs& a, int ib, int jl, bool& 
 // ---------------------------------------------------------------------------
 constexpr int SYM_CHUNK = 8;
 
+// Sub-tile work units for small problems (same idea as pick_split_log2 of the one-sided sweeps): with fewer than four
+// units per CTA a tile is swept in 2 or 4 parts of 4 / 2 rotation rounds.  `units` = tile-units of the launch.
+__host__ __device__ inline int sym_pick_split_log2(long long units, int grid) {
+    if (units >= 4LL * grid) return 0;
+    if (2 * units >= 4LL * grid) return 1;
+    return 2;
+}
+
 struct SymRuns {
     long long rounds;     // complete round-robin rounds of chunks
     long long tail_b, tail_e;
@@ -119,19 +129,20 @@ template <int TPB>
 struct SymCursor {
     long long r, u, u_end;   // current run, current unit, end of the run
     int ib, jl, cnt;
+    // (jl and cnt count sub-units: unit jl of block ib is part jl & (S-1) of the block's tile-unit jl >> split_log2)
     __device__ void open(const SymArgs& a, const SymRuns& R, long long run) {
         r = run;
         R.run(run, u, u_end);
-        ib  = sym_find_block<TPB>(a, u);
-        jl  = static_cast<int>(u - sym_prefix<TPB>(a, ib));
-        cnt = sym_count<TPB>(a, ib);
+        ib  = sym_find_block<TPB>(a, u >> a.split_log2);
+        jl  = static_cast<int>(u - (sym_prefix<TPB>(a, ib) << a.split_log2));
+        cnt = sym_count<TPB>(a, ib) << a.split_log2;
     }
     // make (ib, jl) valid for the current unit (skips exhausted / empty blocks)
     __device__ void settle(const SymArgs& a) {
         while (jl >= cnt) {
             ++ib;
             jl  = 0;
-            cnt = sym_count<TPB>(a, ib);
+            cnt = sym_count<TPB>(a, ib) << a.split_log2;
         }
     }
     // advance by n units inside the current run; opens the next run when this one is exhausted

@@ -38,24 +38,32 @@ inline int sym_run(int smem, int op, const SymArgs* a, int grid, int* out, cudaS
     return (int)cudaGetLastError();
 }
 
-template <int KID>
-inline int dispatch_sym(int prec, int mode, int op, const SymArgs* a, int grid, int* out, cudaStream_t st) {
+template <int KID, bool SUB>
+inline int dispatch_sym_sub(int prec, int mode, int op, const SymArgs* a, int grid, int* out, cudaStream_t st) {
     if (prec == NB_PREC_F64) {
         constexpr int smem = SymF64Smem<SYM_NI_F64>::kTotal;
         switch (mode) {
-            case NB_MODE_FORCE: return sym_run<sym_f64_kernel<KID, NB_MODE_FORCE, SYM_NI_F64, SYM_MINB_F64>>(smem, op, a, grid, out, st);
-            case NB_MODE_POT: return sym_run<sym_f64_kernel<KID, NB_MODE_POT, SYM_NI_F64, SYM_MINB_F64>>(smem, op, a, grid, out, st);
-            case NB_MODE_BOTH: return sym_run<sym_f64_kernel<KID, NB_MODE_BOTH, SYM_NI_F64, SYM_MINB_F64>>(smem, op, a, grid, out, st);
+            case NB_MODE_FORCE: return sym_run<sym_f64_kernel<KID, NB_MODE_FORCE, SYM_NI_F64, SYM_MINB_F64, SUB>>(smem, op, a, grid, out, st);
+            case NB_MODE_POT: return sym_run<sym_f64_kernel<KID, NB_MODE_POT, SYM_NI_F64, SYM_MINB_F64, SUB>>(smem, op, a, grid, out, st);
+            case NB_MODE_BOTH: return sym_run<sym_f64_kernel<KID, NB_MODE_BOTH, SYM_NI_F64, SYM_MINB_F64, SUB>>(smem, op, a, grid, out, st);
         }
     } else {
         constexpr int smem = SymF32Smem<SYM_NP>::kTotal;
         switch (mode) {
-            case NB_MODE_FORCE: return sym_run<sym_f32_kernel<KID, NB_MODE_FORCE, SYM_NP, SYM_MINB_F32>>(smem, op, a, grid, out, st);
-            case NB_MODE_POT: return sym_run<sym_f32_kernel<KID, NB_MODE_POT, SYM_NP, SYM_MINB_F32>>(smem, op, a, grid, out, st);
-            case NB_MODE_BOTH: return sym_run<sym_f32_kernel<KID, NB_MODE_BOTH, SYM_NP, SYM_MINB_F32>>(smem, op, a, grid, out, st);
+            case NB_MODE_FORCE: return sym_run<sym_f32_kernel<KID, NB_MODE_FORCE, SYM_NP, SYM_MINB_F32, SUB>>(smem, op, a, grid, out, st);
+            case NB_MODE_POT: return sym_run<sym_f32_kernel<KID, NB_MODE_POT, SYM_NP, SYM_MINB_F32, SUB>>(smem, op, a, grid, out, st);
+            case NB_MODE_BOTH: return sym_run<sym_f32_kernel<KID, NB_MODE_BOTH, SYM_NP, SYM_MINB_F32, SUB>>(smem, op, a, grid, out, st);
         }
     }
     return NB_E_INVALID_ARG;
+}
+
+// sub-tile work units (a->split_log2 > 0, small problems) are a separate instantiation; the occupancy query uses the
+// whole-tile kernel (the grid only has to be a sensible size: there is no inter-CTA synchronisation)
+template <int KID>
+inline int dispatch_sym(int prec, int mode, int op, const SymArgs* a, int grid, int* out, cudaStream_t st) {
+    if (op == SYM_OP_LAUNCH && a->split_log2 > 0) return dispatch_sym_sub<KID, true>(prec, mode, op, a, grid, out, st);
+    return dispatch_sym_sub<KID, false>(prec, mode, op, a, grid, out, st);
 }
 
 }  // namespace nb

@@ -157,11 +157,13 @@ __device__ __forceinline__ void sym_cold_to_hot(const IState<NP>& S, SymHot32<NP
 // latency (the rotation overlaps the next step's separations) sits on a dependency chain inside an
 // iteration — that matters because only 4 warps share an SM sub-partition at 128 registers per thread.
 // ---------------------------------------------------------------------------
-template <int KID, int MODE, bool U, int NP, typename ST>
+//   SUB: the unit is a part of the tile, steps [t0, t1) (multiples of 32: whole rotation rounds); !SUB: [0, TJ)
+template <int KID, int MODE, bool U, int NP, typename ST, bool SUB>
 __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ stage, ST& S, const f2* mi,
                                              const float* ci0, const float* ci1, const float cmax_i,
                                              const float c_pair, const float eps2, float* __restrict__ jw,
-                                             const int lane) {
+                                             const int lane, const int t0_in, const int t1_in) {
+    const int t0 = SUB ? t0_in : 0, t1 = SUB ? t1_in : TJ;
     const float* __restrict__ sX = reinterpret_cast<const float*>(stage) + COMP_X * TJ;
     const float* __restrict__ sY = reinterpret_cast<const float*>(stage) + COMP_Y * TJ;
     const float* __restrict__ sZ = reinterpret_cast<const float*>(stage) + COMP_Z * TJ;
@@ -178,7 +180,7 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
     float xj, yj, zj, mj = 1.f, cj = c_pair;     // step t
     float xn, yn, zn, mn = 1.f, cn = c_pair;     // step t + 1 (prefetched)
     {
-        const int j0 = rec_index(0), j1 = rec_index(1);
+        const int j0 = rec_index(t0), j1 = rec_index(t0 + 1);
         xj = sX[j0]; yj = sY[j0]; zj = sZ[j0];
         xn = sX[j1]; yn = sY[j1]; zn = sZ[j1];
         if (!U) {
@@ -215,9 +217,9 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
 
     JAcc32 J;
     J.x = J.y = J.z = J.p = 0ull;
-    constexpr int kUnroll = (KID == NB_KERNEL_SPLINE) ? SYM_UNROLL_SPLINE : SYM_UNROLL;
+    constexpr int kUnroll = SUB ? 2 : ((KID == NB_KERNEL_SPLINE) ? SYM_UNROLL_SPLINE : SYM_UNROLL);
 #pragma unroll kUnroll
-    for (int t = 0; t < TJ; ++t) {
+    for (int t = t0; t < t1; ++t) {
         if (KID == NB_KERNEL_SPLINE && exact) {
             // exact step, in place (see sym_tile_f32_spline)
             float jx0, jx1, jy0, jy1, jz0, jz1, jp0, jp1;
@@ -332,11 +334,12 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
 // with the exact step moved out of line through workspace atomics 24.8 ms; the software-pipelined loop
 // 21.8-22.4 ms with the in-place step, 23.3-24.8 ms with the out-of-line ones).
 // ---------------------------------------------------------------------------
-template <int MODE, bool U, int NP, typename ST>
+template <int MODE, bool U, int NP, typename ST, bool SUB>
 __device__ __forceinline__ void sym_tile_f32_spline(const unsigned char* __restrict__ stage, ST& S, const f2* mi,
                                                     const float* ci0, const float* ci1, const float cmax_i,
                                                     const float c_pair, const float eps2, float* __restrict__ jw,
-                                                    const int lane) {
+                                                    const int lane, const int t0_in, const int t1_in) {
+    const int r0 = SUB ? (t0_in >> 5) : 0, r1 = SUB ? (t1_in >> 5) : TJ / 32;   // rotation rounds of this unit
     const float* __restrict__ sX = reinterpret_cast<const float*>(stage) + COMP_X * TJ;
     const float* __restrict__ sY = reinterpret_cast<const float*>(stage) + COMP_Y * TJ;
     const float* __restrict__ sZ = reinterpret_cast<const float*>(stage) + COMP_Z * TJ;
@@ -348,7 +351,7 @@ __device__ __forceinline__ void sym_tile_f32_spline(const unsigned char* __restr
     constexpr int kSteps = (MODE == NB_MODE_BOTH) ? 2 : 1;
 
 #pragma unroll 1
-    for (int rho = 0; rho < TJ / 32; ++rho) {
+    for (int rho = r0; rho < r1; ++rho) {
         JAcc32 J;
         J.x = J.y = J.z = J.p = 0ull;
         const int jb = 32 * rho;
@@ -462,32 +465,33 @@ __device__ __forceinline__ void sym_tile_f32_spline(const unsigned char* __restr
 }
 
 // kernel-id dispatch of the two loop styles
-template <int KID, int MODE, bool U, int NP, typename ST>
+template <int KID, int MODE, bool U, int NP, typename ST, bool SUB>
 __device__ __forceinline__ void sym_tile_f32_any(const unsigned char* __restrict__ stage, ST& S, const f2* mi,
                                                  const float* ci0, const float* ci1, const float cmax_i,
                                                  const float c_pair, const float eps2, float* __restrict__ jw,
-                                                 const int lane) {
+                                                 const int lane, const int t0, const int t1) {
     if constexpr (KID == NB_KERNEL_SPLINE && MODE != NB_MODE_POT)
-        sym_tile_f32_spline<MODE, U, NP, ST>(stage, S, mi, ci0, ci1, cmax_i, c_pair, eps2, jw, lane);
+        sym_tile_f32_spline<MODE, U, NP, ST, SUB>(stage, S, mi, ci0, ci1, cmax_i, c_pair, eps2, jw, lane, t0, t1);
     else
-        sym_tile_f32<KID, MODE, U, NP, ST>(stage, S, mi, ci0, ci1, cmax_i, c_pair, eps2, jw, lane);
+        sym_tile_f32<KID, MODE, U, NP, ST, SUB>(stage, S, mi, ci0, ci1, cmax_i, c_pair, eps2, jw, lane, t0, t1);
 }
 
 // general (per-particle mass / softening) symmetric tile: rare (species boundaries, per-particle softening
 // arrays, padding) -> non-inlined, re-reads the i-particles' masses and softening terms from the packed
 // records and works on a copy of the hot state
-template <int KID, int MODE, int NP>
+template <int KID, int MODE, int NP, bool SUB>
 __device__ __noinline__ void sym_tile_f32_general(const unsigned char* stage, SymHot32<NP>* H,
                                                   const unsigned char* packed, const long long ig0,
                                                   const long long i_end, const float eps2, float* jw,
-                                                  const int lane) {
+                                                  const int lane, const int t0, const int t1) {
     SymCold32<NP> T;
     sym_hot_to_cold<NP>(*H, T.S);
     sym_load_mc<NP>(packed, ig0, i_end, T);
     float cmax_i = 0.f;
 #pragma unroll
     for (int q = 0; q < NP; ++q) cmax_i = fmaxf(cmax_i, fmaxf(T.S.c0[q], T.S.c1[q]));
-    sym_tile_f32_any<KID, MODE, false, NP, IState<NP>>(stage, T.S, T.m, T.S.c0, T.S.c1, cmax_i, 0.f, eps2, jw, lane);
+    sym_tile_f32_any<KID, MODE, false, NP, IState<NP>, SUB>(stage, T.S, T.m, T.S.c0, T.S.c1, cmax_i, 0.f, eps2, jw, lane,
+                                                            t0, t1);
     sym_cold_to_hot<NP>(T.S, *H);
 }
 
@@ -496,11 +500,11 @@ template <int KID, int MODE, int NP>
 __device__ __noinline__ void sym_tile_f32_diag(const unsigned char* stage, SymHot32<NP>* H,
                                                const unsigned char* packed, const long long ig0,
                                                const long long i_end, const float eps2, const long long jg0,
-                                               const long long n_j) {
+                                               const long long n_j, const int t0, const int t1) {
     SymCold32<NP> T;
     sym_hot_to_cold<NP>(*H, T.S);
     sym_load_mc<NP>(packed, ig0, i_end, T);
-    tile_f32<KID, MODE, true, false, false, NP, 4>(stage, T.S, eps2, 0.f, jg0, ig0, n_j);
+    tile_f32<KID, MODE, true, false, false, NP, 4>(stage, T.S, eps2, 0.f, jg0, ig0, n_j, t0, t1);
     sym_cold_to_hot<NP>(T.S, *H);
 }
 
@@ -515,7 +519,9 @@ struct SymF32Smem {
     static constexpr int kTotal      = kJOff + kJBytes;
 };
 
-template <int KID, int MODE, int NP, int MINB>
+//   SUB = true: sub-tile work units (a.split_log2 > 0, small problems), a separate instantiation so that the
+//   whole-tile kernels keep constant loop bounds
+template <int KID, int MODE, int NP, int MINB, bool SUB = false>
 __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     using L = SymF32Smem<NP>;
@@ -549,7 +555,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
     auto issue_next = [&]() {
         prod->settle(a);
         bool dg;
-        const int gt  = sym_tile<TPB>(a, prod->ib, prod->jl, dg);
+        const int gt  = sym_tile<TPB>(a, prod->ib, prod->jl >> (SUB ? a.split_log2 : 0), dg);
         uint64_t* bar = &full_bar[issued % STAGES];
         mbar_expect_tx(bar, TILE_BYTES_F32);
         bulk_g2s(smem + (issued % STAGES) * TILE_BYTES_F32, a.packed + static_cast<size_t>(gt) * TILE_BYTES_F32, TILE_BYTES_F32, bar);
@@ -563,11 +569,11 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
 
     // j side of the previous symmetric tile: summed over the warps and added to ws after the next barrier
     bool pend = false;
-    int pend_gt = 0;
+    int pend_gt = 0, pend_t0 = 0, pend_t1 = TJ;
     float pend_scale = 1.f;
     auto flush_j = [&]() {
 #pragma unroll
-        for (int jj = tid; jj < TJ; jj += THREADS) {
+        for (int jj = (SUB ? pend_t0 : 0) + tid; jj < (SUB ? pend_t1 : TJ); jj += THREADS) {
             double* dst = a.ws + (static_cast<size_t>(pend_gt) * TJ + jj) * 4;
 #pragma unroll
             for (int comp = 0; comp < 4; ++comp) {
@@ -657,26 +663,30 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f32_kernel(const SymArgs a)
             mbar_wait(&full_bar[k % STAGES], (k / STAGES) & 1);
 
             bool diag;
-            const int gt = sym_tile<TPB>(a, ib, jl, diag);
+            const int sl = SUB ? a.split_log2 : 0;
+            const int gt = sym_tile<TPB>(a, ib, jl >> sl, diag);
+            const int t0 = (jl & ((1 << sl) - 1)) * (TJ >> sl), t1 = t0 + (TJ >> sl);   // this unit's steps of the tile
             const unsigned char* stage = smem + (k % STAGES) * TILE_BYTES_F32;
             const float4 meta = *reinterpret_cast<const float4*>(stage + 5 * TJ * 4);   // {c_uni|NaN, m_uni|NaN, c_max, -}
             float m_fold = 1.f;
             if (diag) {
                 sym_tile_f32_diag<KID, MODE, NP>(stage, &S, a.packed, ig0, i_end, eps2, static_cast<long long>(gt) * TJ,
-                                                 a.n_j);
+                                                 a.n_j, SUB ? t0 : 0, SUB ? t1 : TJ);
             } else {
                 float* jw = jbuf + warp * 4 * TJ;
                 if (blk_uni && meta.x == meta.x && meta.y == meta.y) {
                     m_fold     = meta.y;
                     pend_scale = mI;
-                    sym_tile_f32_any<KID, MODE, true, NP, SymHot32<NP>>(stage, S, nullptr, nullptr, nullptr, 0.f,
-                                                                         fmaxf(cI, meta.x), eps2, jw, lane);
+                    sym_tile_f32_any<KID, MODE, true, NP, SymHot32<NP>, SUB>(stage, S, nullptr, nullptr, nullptr, 0.f,
+                                                                              fmaxf(cI, meta.x), eps2, jw, lane, t0, t1);
                 } else {
                     pend_scale = 1.f;
-                    sym_tile_f32_general<KID, MODE, NP>(stage, &S, a.packed, ig0, i_end, eps2, jw, lane);
+                    sym_tile_f32_general<KID, MODE, NP, SUB>(stage, &S, a.packed, ig0, i_end, eps2, jw, lane, t0, t1);
                 }
                 pend    = true;
                 pend_gt = gt;
+                pend_t0 = t0;
+                pend_t1 = t1;
             }
 
             // fold this tile's partial sums (x tile mass) into the float running sums

@@ -95,10 +95,13 @@ struct SymCold64 {
 };
 
 // one symmetric j-tile; jw = this warp's slice [4][TJ] of the j-side buffer
-template <int KID, int MODE, bool U, int NI>
+//   SUB: the unit is a part of the tile, steps [t0, t1) (whole rotation rounds); !SUB: the whole tile
+template <int KID, int MODE, bool U, int NI, bool SUB>
 __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ stage, IState64<NI>& S,
                                              const double (&mi)[NI], const double cmax_i, const double c_pair,
-                                             const double eps2, double* __restrict__ jw, const int lane) {
+                                             const double eps2, double* __restrict__ jw, const int lane,
+                                             const int t0_in, const int t1_in) {
+    const int r0 = SUB ? (t0_in >> 5) : 0, r1 = SUB ? (t1_in >> 5) : TJ / 32;   // rotation rounds of this unit
     const double* __restrict__ sX = reinterpret_cast<const double*>(stage) + COMP_X * TJ;
     const double* __restrict__ sY = reinterpret_cast<const double*>(stage) + COMP_Y * TJ;
     const double* __restrict__ sZ = reinterpret_cast<const double*>(stage) + COMP_Z * TJ;
@@ -109,7 +112,7 @@ __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ s
     const int src = (lane + 1) & 31;
 
 #pragma unroll 1
-    for (int rho = 0; rho < TJ / 32; ++rho) {
+    for (int rho = r0; rho < r1; ++rho) {
         JAcc64 J;
         J.x = J.y = J.z = J.p = 0.0;
         const int jb = 32 * rho;
@@ -195,22 +198,24 @@ __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ s
     }
 }
 
-template <int KID, int MODE, int NI>
+template <int KID, int MODE, int NI, bool SUB>
 __device__ __noinline__ void sym_tile_f64_general(const unsigned char* stage, SymCold64<NI>* T, const double cmax_i,
-                                                  const double eps2, double* jw, const int lane) {
+                                                  const double eps2, double* jw, const int lane, const int t0,
+                                                  const int t1) {
     IState64<NI> S = T->S;   // work on registers, not on the caller's local-memory copy
     double m[NI];
 #pragma unroll
     for (int q = 0; q < NI; ++q) m[q] = T->m[q];
-    sym_tile_f64<KID, MODE, false, NI>(stage, S, m, cmax_i, 0.0, eps2, jw, lane);
+    sym_tile_f64<KID, MODE, false, NI, SUB>(stage, S, m, cmax_i, 0.0, eps2, jw, lane, t0, t1);
     T->S = S;
 }
 
 // diagonal tile (overlaps the CTA's own i-block): one-sided masked path of nb_sweep_f64.cuh on a state copy
 template <int KID, int MODE, int NI>
 __device__ __noinline__ void sym_tile_f64_diag(const unsigned char* stage, IState64<NI>* T, const double eps2,
-                                               const long long jg0, const long long ig0, const long long n_j) {
-    tile_f64<KID, MODE, true, false, false, NI>(stage, *T, eps2, 0.0, jg0, ig0, n_j);
+                                               const long long jg0, const long long ig0, const long long n_j,
+                                               const int t0, const int t1) {
+    tile_f64<KID, MODE, true, false, false, NI>(stage, *T, eps2, 0.0, jg0, ig0, n_j, t0, t1);
 }
 
 template <int NI>
@@ -224,7 +229,7 @@ struct SymF64Smem {
     static constexpr int kTotal      = kJOff + kJBytes;
 };
 
-template <int KID, int MODE, int NI, int MINB>
+template <int KID, int MODE, int NI, int MINB, bool SUB = false>
 __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     using L = SymF64Smem<NI>;
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a)
     auto issue_next = [&]() {
         prod->settle(a);
         bool dg;
-        const int gt  = sym_tile<TPB>(a, prod->ib, prod->jl, dg);
+        const int gt  = sym_tile<TPB>(a, prod->ib, prod->jl >> (SUB ? a.split_log2 : 0), dg);
         uint64_t* bar = &full_bar[issued % NSTG];
         mbar_expect_tx(bar, TILE_BYTES_F64);
         bulk_g2s(smem + (issued % NSTG) * TILE_BYTES_F64, a.packed + static_cast<size_t>(gt) * TILE_BYTES_F64, TILE_BYTES_F64, bar);
@@ -272,11 +277,11 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a)
     }
 
     bool pend = false;
-    int pend_gt = 0;
+    int pend_gt = 0, pend_t0 = 0, pend_t1 = TJ;
     double pend_scale = 1.0;
     auto flush_j = [&]() {
 #pragma unroll
-        for (int jj = tid; jj < TJ; jj += THREADS) {
+        for (int jj = (SUB ? pend_t0 : 0) + tid; jj < (SUB ? pend_t1 : TJ); jj += THREADS) {
             double* dst = a.ws + (static_cast<size_t>(pend_gt) * TJ + jj) * 4;
 #pragma unroll
             for (int comp = 0; comp < 4; ++comp) {
@@ -350,31 +355,36 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a)
             mbar_wait(&full_bar[k % NSTG], (k / NSTG) & 1);
 
             bool diag;
-            const int gt = sym_tile<TPB>(a, ib, jl, diag);
+            const int sl = SUB ? a.split_log2 : 0;
+            const int gt = sym_tile<TPB>(a, ib, jl >> sl, diag);
+            const int t0 = (jl & ((1 << sl) - 1)) * (TJ >> sl), t1 = t0 + (TJ >> sl);   // this unit's steps of the tile
             const unsigned char* stage = smem + (k % NSTG) * TILE_BYTES_F64;
             const double2 meta = *reinterpret_cast<const double2*>(stage + 5 * TJ * 8);   // {c_uni, m_uni} or NaN
             double m_fold = 1.0;
             if (diag) {
                 IState64<NI> T = S;
-                sym_tile_f64_diag<KID, MODE, NI>(stage, &T, eps2, static_cast<long long>(gt) * TJ, ig0, a.n_j);
+                sym_tile_f64_diag<KID, MODE, NI>(stage, &T, eps2, static_cast<long long>(gt) * TJ, ig0, a.n_j,
+                                                 SUB ? t0 : 0, SUB ? t1 : TJ);
                 S = T;
             } else {
                 double* jw = jbuf + warp * 4 * TJ;
                 if (blk_uni && meta.x == meta.x && meta.y == meta.y) {
                     m_fold     = meta.y;
                     pend_scale = mI;
-                    sym_tile_f64<KID, MODE, true, NI>(stage, S, mi, cmax_i, fmax(cI, meta.x), eps2, jw, lane);
+                    sym_tile_f64<KID, MODE, true, NI, SUB>(stage, S, mi, cmax_i, fmax(cI, meta.x), eps2, jw, lane, t0, t1);
                 } else {
                     pend_scale = 1.0;
                     SymCold64<NI> T;
                     T.S = S;
 #pragma unroll
                     for (int q = 0; q < NI; ++q) T.m[q] = mi[q];
-                    sym_tile_f64_general<KID, MODE, NI>(stage, &T, cmax_i, eps2, jw, lane);
+                    sym_tile_f64_general<KID, MODE, NI, SUB>(stage, &T, cmax_i, eps2, jw, lane, t0, t1);
                     S = T.S;
                 }
                 pend    = true;
                 pend_gt = gt;
+                pend_t0 = t0;
+                pend_t1 = t1;
             }
 #pragma unroll
             for (int q = 0; q < NI; ++q) {

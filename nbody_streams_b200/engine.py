@@ -242,7 +242,7 @@ class DirectEngine:
 
         # pair-symmetric sweep (every unordered pair once, partial sums of BOTH particles; large N) or the
         # one-sided sweep (bitwise reproducible, finer work units; small N)
-        self.symmetric = use_symmetric(self.N, algorithm)
+        self.symmetric = use_symmetric(self.N, algorithm, self.world)
         self._sym_ws = None
         self._sym_out = None
         self.first = self.layout.first(self.rank)

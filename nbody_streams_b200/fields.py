@@ -195,12 +195,18 @@ def _grid_for(prec: int, kernel_id: int, mode: int, device, sym: bool = False) -
     return g
 
 
-def use_symmetric(N: int, algorithm: str | None = None) -> bool:
+SYM_MIN_N_MULTI_RANK = 32768
+
+
+def use_symmetric(N: int, algorithm: str | None = None, world: int = 1) -> bool:
     """Which sweep evaluates an all-pairs problem of N particles: the pair-symmetric one (every unordered
     pair once, applied to both particles; large N) or the one-sided one (every ordered pair, bitwise
-    reproducible, finer work units; small N).  `algorithm`: None/'auto', 'symmetric' or 'onesided'."""
+    reproducible, finer work units; small N).  `algorithm`: None/'auto', 'symmetric' or 'onesided'.
+    'auto' switches at nb_sym_min_n() particles (8192) on one rank and at 32768 on several ranks, where the
+    symmetric path adds a reduce-scatter and each rank's launches are 1/world of the work."""
     if algorithm in (None, "auto"):
-        return N >= _lib.load().nb_sym_min_n()
+        n0 = _lib.load().nb_sym_min_n()
+        return N >= (n0 if world == 1 else max(n0, SYM_MIN_N_MULTI_RANK))
     if algorithm not in ("symmetric", "onesided"):
         raise ValueError(f"algorithm must be 'auto', 'symmetric' or 'onesided', got {algorithm!r}")
     return algorithm == "symmetric"
@@ -316,7 +322,7 @@ def _run_direct(pos_t, mass_t, mass_scalar, h_t, h_scalar, N, prec, kernel_id, m
     phi = phi_buf[:n_i] if phi_buf is not None else None
     if N == 0:
         return acc, phi
-    sym = n_sources is None and use_symmetric(N, algorithm)
+    sym = n_sources is None and use_symmetric(N, algorithm, world)
     # sources restricted to the first n_sources particles on ONE rank: still pair-symmetric — the pairs inside the
     # source set once (triangle over the source tiles), and (test-particle tiles) x (source tiles) as a rectangle whose
     # j-side contributions vanish with the test particles' zero masses

@@ -171,6 +171,7 @@ def test_auto_selection_threshold(nb):
     n0 = lib.nb_sym_min_n()
     assert n0 > 0
     assert use_symmetric(n0) and not use_symmetric(n0 - 1)
+    assert not use_symmetric(n0, world=2) and use_symmetric(32768, world=2)     # several ranks: from 32768 on
     assert use_symmetric(10, "symmetric") and not use_symmetric(10**7, "onesided")
     with pytest.raises(ValueError):
         use_symmetric(10, "both")
