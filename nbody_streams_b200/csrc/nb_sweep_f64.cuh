@@ -6,7 +6,8 @@
 // Same persistent stream-K / TMA-ring structure as the f32 sweep; the pair
 // arithmetic is scalar DFMA with NI i-particles register-blocked per thread and
 // a hand-rolled full-precision rsqrt (MUFU.RSQ64H seed + one third-order step,
-// 5 FP64 ops) instead of the library's longer sequence.  Bound: FP64 pipe.
+// 5 FP64 ops; force-only sweeps take r^-3 directly from the seed, 6 ops instead
+// of 5 + 2) instead of the library's longer sequence.  Bound: FP64 pipe.
 #pragma once
 #include "nb_sweep.cuh"
 
@@ -40,6 +41,14 @@ __device__ __forceinline__ void pair_f64(const double xj, const double yj, const
     if (KID == NB_KERNEL_SPLINE) {
         inside = (d < h2) && (!MASK || valid);
         d = fmax(d, h2);
+    }
+    if (MODE == NB_MODE_FORCE && (KID == NB_KERNEL_NEWTONIAN || KID == NB_KERNEL_PLUMMER)) {   // only r^-3 is needed
+        const double w = rsqrt3_f64(d);
+        const double f = (UM && !MASK) ? w : mj * w;
+        ax = fma(f, dx, ax);
+        ay = fma(f, dy, ay);
+        az = fma(f, dz, az);
+        return;
     }
     const double rinv = rsqrt_f64(d);
     const double mr   = (UM && !MASK) ? rinv : mj * rinv;
@@ -206,11 +215,17 @@ __device__ __forceinline__ void tile_f64_spline(const unsigned char* __restrict_
             for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
                 for (int q = 0; q < NI; ++q) {
-                    const double rinv = rsqrt_f64(d[jj][q]);
-                    const double mr   = UM ? rinv : ms[jj] * rinv;
-                    if (MODE & NB_MODE_POT) S.sp[q] += mr;
+                    double f;
+                    if (MODE == NB_MODE_FORCE) {   // only r^-3 is needed
+                        const double w = rsqrt3_f64(d[jj][q]);
+                        f = UM ? w : ms[jj] * w;
+                    } else {
+                        const double rinv = rsqrt_f64(d[jj][q]);
+                        const double mr   = UM ? rinv : ms[jj] * rinv;
+                        S.sp[q] += mr;
+                        f = mr * (rinv * rinv);
+                    }
                     if (MODE & NB_MODE_FORCE) {
-                        const double f = mr * (rinv * rinv);
                         S.ax[q] = fma(f, dx[jj][q], S.ax[q]);
                         S.ay[q] = fma(f, dy[jj][q], S.ay[q]);
                         S.az[q] = fma(f, dz[jj][q], S.az[q]);

@@ -12,7 +12,10 @@ enum { SYM_OP_LAUNCH = 0, SYM_OP_QUERY = 1 };
 #define NB_SYM_MINB_F32 4
 #endif
 constexpr int SYM_MINB_F32 = NB_SYM_MINB_F32;   // resident CTAs / SM the f32 kernel is compiled for (4: <= 128 registers)
-constexpr int SYM_MINB_F64 = 3;
+#ifndef NB_SYM_MINB_F64
+#define NB_SYM_MINB_F64 4
+#endif
+constexpr int SYM_MINB_F64 = NB_SYM_MINB_F64;
 
 // cudaFuncSetAttribute is needed once per (kernel, device), not per launch
 template <auto KERN>

@@ -14,9 +14,18 @@
 
 namespace nb {
 
-constexpr int SYM_NI_F64     = 4;                       // i-particles per thread
+#ifndef NB_SYM_NI_F64
+#define NB_SYM_NI_F64 4
+#endif
+#ifndef NB_SYM_F64_DIRECT
+#define NB_SYM_F64_DIRECT 1
+#endif
+constexpr int SYM_NI_F64     = NB_SYM_NI_F64;           // i-particles per thread
 constexpr int SYM_IB_F64     = THREADS * SYM_NI_F64;    // 512 per CTA
 constexpr int SYM_TPB_F64    = SYM_IB_F64 / TJ;         // 2 tiles per i-block
+// j-side sums: DIRECT = every warp adds its 32 travelling accumulators to the workspace after each rotation round
+// (RED.E.ADD.F64 from registers); otherwise per-warp slices in shared memory, reduced and added once per tile
+constexpr bool SYM_F64_DIRECT = NB_SYM_F64_DIRECT != 0;
 constexpr int SYM_STAGES_F64 = 2;                       // a tile takes ~40k cycles to sweep: one tile of prefetch is plenty
 #ifndef NB_SYM_UNROLL_F64
 #define NB_SYM_UNROLL_F64 2
@@ -38,11 +47,17 @@ struct JAcc64 {
 template <int KID, int MODE>
 __device__ __forceinline__ void sym_factors_f64(const double d, const double h2, const double eps2, double& w,
                                                 double& p) {
+    constexpr bool kDehnen = (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
+    if (!kDehnen && MODE == NB_MODE_FORCE) {   // only r^-3 is needed
+        w = rsqrt3_f64(d);
+        p = 0.0;
+        return;
+    }
     const double rinv  = rsqrt_f64(d);
     const double rinv2 = rinv * rinv;
     p = rinv;
     w = 0.0;
-    if (KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2) {
+    if (kDehnen) {
         const double t = (h2 - eps2) * rinv2;   // c = h^2 + eps2 seeds the r^2 chain; the terms use bare h^2
         if (MODE & NB_MODE_POT)
             p = rinv * ((KID == NB_KERNEL_DEHNEN_K1) ? fma(0.5, t, 1.0) : fma(t, fma(0.375, t, 0.5), 1.0));
@@ -51,6 +66,19 @@ __device__ __forceinline__ void sym_factors_f64(const double d, const double h2,
     } else if (MODE & NB_MODE_FORCE) {
         w = rinv * rinv2;
     }
+}
+
+// acc += f * d for both sides of a pair.  A DFMA that reads three different registers takes 3 issue cycles, 2 when
+// operands come from the reuse cache (nb_ubench 17-20); ptxas pairs the two accumulates that share f and d whatever
+// the source order is (an asm block with the six in the ideal order produced the same SASS).
+__device__ __forceinline__ void sym_acc6_f64(const double fi, const double fj, const double dx, const double dy,
+                                             const double dz, double& ax, double& ay, double& az, JAcc64& J) {
+    ax  = fma(dx, fi, ax);
+    J.x = fma(dx, fj, J.x);
+    ay  = fma(dy, fi, ay);
+    J.y = fma(dy, fj, J.y);
+    az  = fma(dz, fi, az);
+    J.z = fma(dz, fj, J.z);
 }
 
 template <int MODE, bool U>
@@ -62,28 +90,13 @@ __device__ __forceinline__ void sym_apply_f64(const double w, const double p, co
             sp += p;
             J.p += p;
         }
-        if (MODE & NB_MODE_FORCE) {
-            ax  = fma(w, dx, ax);
-            ay  = fma(w, dy, ay);
-            az  = fma(w, dz, az);
-            J.x = fma(w, dx, J.x);
-            J.y = fma(w, dy, J.y);
-            J.z = fma(w, dz, J.z);
-        }
+        if (MODE & NB_MODE_FORCE) sym_acc6_f64(w, w, dx, dy, dz, ax, ay, az, J);
     } else {
         if (MODE & NB_MODE_POT) {
             sp  = fma(mj, p, sp);
             J.p = fma(mi, p, J.p);
         }
-        if (MODE & NB_MODE_FORCE) {
-            const double fi = mj * w, fj = mi * w;
-            ax  = fma(fi, dx, ax);
-            ay  = fma(fi, dy, ay);
-            az  = fma(fi, dz, az);
-            J.x = fma(fj, dx, J.x);
-            J.y = fma(fj, dy, J.y);
-            J.z = fma(fj, dz, J.z);
-        }
+        if (MODE & NB_MODE_FORCE) sym_acc6_f64(mj * w, mi * w, dx, dy, dz, ax, ay, az, J);
     }
 }
 
@@ -100,7 +113,8 @@ template <int KID, int MODE, bool U, int NI, bool SUB>
 __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ stage, IState64<NI>& S,
                                              const double (&mi)[NI], const double cmax_i, const double c_pair,
                                              const double eps2, double* __restrict__ jw, const int lane,
-                                             const int t0_in, const int t1_in) {
+                                             const int t0_in, const int t1_in, double* __restrict__ wsj = nullptr,
+                                             const double scale = 1.0) {
     const int r0 = SUB ? (t0_in >> 5) : 0, r1 = SUB ? (t1_in >> 5) : TJ / 32;   // rotation rounds of this unit
     const double* __restrict__ sX = reinterpret_cast<const double*>(stage) + COMP_X * TJ;
     const double* __restrict__ sY = reinterpret_cast<const double*>(stage) + COMP_Y * TJ;
@@ -174,10 +188,9 @@ __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ s
                 } else {
 #pragma unroll
                     for (int q = 0; q < NI; ++q) {
-                        const double rinv = rsqrt_f64(d[q]);
-                        const double w    = (MODE & NB_MODE_FORCE) ? rinv * (rinv * rinv) : 0.0;
-                        sym_apply_f64<MODE, U>(w, rinv, dx[q], dy[q], dz[q], mj, mi[q], S.ax[q], S.ay[q], S.az[q],
-                                               S.sp[q], J);
+                        double w, p;
+                        sym_factors_f64<NB_KERNEL_NEWTONIAN, MODE>(d[q], 0.0, 0.0, w, p);
+                        sym_apply_f64<MODE, U>(w, p, dx[q], dy[q], dz[q], mj, mi[q], S.ax[q], S.ay[q], S.az[q], S.sp[q], J);
                     }
                 }
             }
@@ -189,24 +202,34 @@ __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ s
             }
             if (MODE & NB_MODE_POT) J.p = shfl_d(J.p, src);
         }
-        if (MODE & NB_MODE_FORCE) {
-            jw[0 * TJ + jb + lane] = J.x;
-            jw[1 * TJ + jb + lane] = J.y;
-            jw[2 * TJ + jb + lane] = J.z;
+        if (SYM_F64_DIRECT) {
+            double* dst = wsj + (jb + lane) * 4;   // a_j += -m_i K dx ; s_phi_j += m_i / r
+            if (MODE & NB_MODE_FORCE) {
+                atomicAdd(dst + 0, -J.x * scale);
+                atomicAdd(dst + 1, -J.y * scale);
+                atomicAdd(dst + 2, -J.z * scale);
+            }
+            if (MODE & NB_MODE_POT) atomicAdd(dst + 3, J.p * scale);
+        } else {
+            if (MODE & NB_MODE_FORCE) {
+                jw[0 * TJ + jb + lane] = J.x;
+                jw[1 * TJ + jb + lane] = J.y;
+                jw[2 * TJ + jb + lane] = J.z;
+            }
+            if (MODE & NB_MODE_POT) jw[3 * TJ + jb + lane] = J.p;
         }
-        if (MODE & NB_MODE_POT) jw[3 * TJ + jb + lane] = J.p;
     }
 }
 
 template <int KID, int MODE, int NI, bool SUB>
 __device__ __noinline__ void sym_tile_f64_general(const unsigned char* stage, SymCold64<NI>* T, const double cmax_i,
                                                   const double eps2, double* jw, const int lane, const int t0,
-                                                  const int t1) {
+                                                  const int t1, double* wsj) {
     IState64<NI> S = T->S;   // work on registers, not on the caller's local-memory copy
     double m[NI];
 #pragma unroll
     for (int q = 0; q < NI; ++q) m[q] = T->m[q];
-    sym_tile_f64<KID, MODE, false, NI, SUB>(stage, S, m, cmax_i, 0.0, eps2, jw, lane, t0, t1);
+    sym_tile_f64<KID, MODE, false, NI, SUB>(stage, S, m, cmax_i, 0.0, eps2, jw, lane, t0, t1, wsj, 1.0);
     T->S = S;
 }
 
@@ -225,7 +248,7 @@ struct SymF64Smem {
     static constexpr int kRunOff     = kBarOff + 128;   // mbarriers + the TMA producer's unit cursor
     static constexpr int kRunBytes   = 4 * NI * THREADS * 8;              // double running sums [4][NI][THREADS]
     static constexpr int kJOff       = kRunOff + kRunBytes;
-    static constexpr int kJBytes     = (THREADS / 32) * 4 * TJ * 8;       // j-side slices [warps][4][TJ]
+    static constexpr int kJBytes     = SYM_F64_DIRECT ? 0 : (THREADS / 32) * 4 * TJ * 8;   // j-side slices [warps][4][TJ]
     static constexpr int kTotal      = kJOff + kJBytes;
 };
 
@@ -347,7 +370,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a)
             const int jl = jl0 + t;
             __syncthreads();   // everyone is done with tile k-1: its stage may be refilled, its j-slices are complete
             if (tid == 0 && issued < n_units) issue_next();
-            if (pend) {
+            if (!SYM_F64_DIRECT && pend) {
                 flush_j();
                 __syncthreads();
                 pend = false;
@@ -367,21 +390,23 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_f64_kernel(const SymArgs a)
                                                  SUB ? t0 : 0, SUB ? t1 : TJ);
                 S = T;
             } else {
-                double* jw = jbuf + warp * 4 * TJ;
+                double* jw  = jbuf + warp * 4 * TJ;
+                double* wsj = a.ws + static_cast<size_t>(gt) * TJ * 4;
                 if (blk_uni && meta.x == meta.x && meta.y == meta.y) {
                     m_fold     = meta.y;
                     pend_scale = mI;
-                    sym_tile_f64<KID, MODE, true, NI, SUB>(stage, S, mi, cmax_i, fmax(cI, meta.x), eps2, jw, lane, t0, t1);
+                    sym_tile_f64<KID, MODE, true, NI, SUB>(stage, S, mi, cmax_i, fmax(cI, meta.x), eps2, jw, lane, t0, t1,
+                                                           wsj, mI);
                 } else {
                     pend_scale = 1.0;
                     SymCold64<NI> T;
                     T.S = S;
 #pragma unroll
                     for (int q = 0; q < NI; ++q) T.m[q] = mi[q];
-                    sym_tile_f64_general<KID, MODE, NI, SUB>(stage, &T, cmax_i, eps2, jw, lane, t0, t1);
+                    sym_tile_f64_general<KID, MODE, NI, SUB>(stage, &T, cmax_i, eps2, jw, lane, t0, t1, wsj);
                     S = T.S;
                 }
-                pend    = true;
+                pend    = !SYM_F64_DIRECT;
                 pend_gt = gt;
                 pend_t0 = t0;
                 pend_t1 = t1;

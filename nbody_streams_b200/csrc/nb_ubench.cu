@@ -229,6 +229,36 @@ __global__ void __launch_bounds__(256) ubench_kernel(float* out, int iters, floa
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) s += lo_of(acc[k][cc]) + hi_of(acc[k][cc]);
         out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else if (WHICH >= 17 && WHICH <= 20) {
+        // FP64 operand-count probes (12 independent chains each):
+        //   17: acc = fma(f, d, acc)   three distinct 64-bit registers, f shared by a trio (the sweep's accumulates)
+        //   18: acc = fma(d, d, acc)   two distinct registers (the r^2 chain)
+        //   19: acc = fma(f, d, acc)   three distinct registers, nothing shared
+        //   20: acc = d - acc          DADD, two distinct registers
+        double f[12], d[12], acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            f[k]   = 1.0 + 1e-9 * (t + k);
+            d[k]   = 1e-3 * (t - k);
+            acc[k] = 0.0;
+            asm volatile("" : "+d"(f[k]), "+d"(d[k]));   // opaque: keep them in their own registers
+        }
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    if (WHICH == 17) acc[k] = fma(f[k / 3], d[k], acc[k]);
+                    if (WHICH == 18) acc[k] = fma(d[k], d[k], acc[k]);
+                    if (WHICH == 19) acc[k] = fma(f[k], d[k], acc[k]);
+                    if (WHICH == 20) acc[k] = d[k] - acc[k];
+                }
+        }
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s += acc[k];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = static_cast<float>(s);
     } else if (WHICH == 7) {   // DFMA
         double a[UB_CHAINS];
         const double b = 1.0 + t * 1e-3, c = t * 1e-3;
@@ -305,6 +335,11 @@ int nb_ubench_impl(int which, int iters, double* lane_ops_per_s, double* ms_out)
         case 14: rc = run_ubench<14>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 16.0; break;
         case 15: rc = run_ubench<15>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 16.0; break;
         case 16: rc = run_ubench<16>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 2 * 48.0; break;
+        // FP64 operand-count probes: FP64 lane-ops (4 rounds x 12 chains)
+        case 17: rc = run_ubench<17>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 48.0; break;
+        case 18: rc = run_ubench<18>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 48.0; break;
+        case 19: rc = run_ubench<19>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 48.0; break;
+        case 20: rc = run_ubench<20>(iters, ctas, buf, &ms, 0); ops_per_thread_iter = 48.0; break;
         default: rc = NB_E_INVALID_ARG;
     }
     cudaFree(buf);
