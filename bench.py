@@ -331,9 +331,14 @@ def main():
                        "region; MEASURED_PEAKS.json carries no FP32/FP64 CUDA-core figure",
         "peak_nominal": nominal, "frac_of_nominal": achieved_tf / nominal,
         "flops_per_interaction": FLOPS_PER_INTERACTION,
-        "note": "achieved = 20 flop x ordered pairs delivered / launch time (the reference's N^2 convention); the "
-                "symmetric sweep executes 16 packed FP32 instructions per two interactions where the one-sided "
-                "sweep executes 24, so its FP32-pipe utilisation (ncu, profiles/) is lower than this fraction",
+        "note": ("achieved = 20 flop x ordered pairs delivered / launch time (the reference's N^2 convention); the "
+                 "symmetric sweep executes 16 packed FP32 instructions per two interactions where the one-sided "
+                 "sweep executes 24, so its FP32-pipe utilisation (ncu, profiles/) is lower than this fraction")
+                if args.precision != "float64" else
+                ("achieved = 20 flop x ordered pairs delivered / launch time (the reference's N^2 convention); the "
+                 "symmetric sweep executes 18 (force) / 21 (force+potential) FP64 instructions per two interactions, "
+                 "the one-sided sweep 2 x 15-17; a DFMA reading three different registers takes 3 issue cycles, not 2 "
+                 "(profiles/r02_ubench_f64.md), which is what the FP64 pipe-active figure in profiles/ reflects"),
         "launch_ms_avg": sweep_total_ms / max(1, len(sweep_ms)), "launches_timed": len(sweep_ms),
         "launch_ms": [{"slot": k, "what": sweep_tags[k] if k < len(sweep_tags) else None, "ms_rank0": slot_ms[k],
                        "ms_max_over_ranks": slot_ms_max[k]} for k in range(per_step)],
@@ -343,7 +348,7 @@ def main():
         "traffic": traffic,
         "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic bytes per launch: 20 MB of records read "
                         "+ 32 MB of double partial sums (L2-resident, atomically updated) for 2e13 algorithmic flop "
-                        "-> FP32-pipe bound",
+                        "-> " + ("FP32" if args.precision != "float64" else "FP64") + "-pipe bound",
     }
 
     # ---- parity (outside the timed region): rank 0's first rows after the last step against the float64 oracle
