@@ -175,17 +175,20 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
     const f2 ceps = splat(eps2);
     const int src = (lane + 1) & 31;
 
-    // record of step t: particle 32 (t / 32) + (lane + t) mod 32 of the tile
-    auto rec_index = [&](int t) { return (t & (TJ - 32)) + ((lane + t) & 31); };
+    // record of step t: particle 32 (t / 32) + (lane + t) mod 32 of the tile.  Its BYTE offset inside a component
+    // array is ((4 lane + 4 t) & 124) | (4 t & 0x380): the first term comes from a running per-thread counter (one add
+    // with an immediate + one and-or per step), the second is uniform and changes once per rotation round.
+    auto rec_off = [&](int t) { return ((4 * lane + 4 * t) & 124) | ((4 * t) & (4 * (TJ - 32))); };
+    auto ldf = [&](const float* base, int off) { return *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(base) + off); };
     float xj, yj, zj, mj = 1.f, cj = c_pair;     // step t
     float xn, yn, zn, mn = 1.f, cn = c_pair;     // step t + 1 (prefetched)
     {
-        const int j0 = rec_index(t0), j1 = rec_index(t0 + 1);
-        xj = sX[j0]; yj = sY[j0]; zj = sZ[j0];
-        xn = sX[j1]; yn = sY[j1]; zn = sZ[j1];
+        const int j0 = rec_off(t0), j1 = rec_off(t0 + 1);
+        xj = ldf(sX, j0); yj = ldf(sY, j0); zj = ldf(sZ, j0);
+        xn = ldf(sX, j1); yn = ldf(sY, j1); zn = ldf(sZ, j1);
         if (!U) {
-            mj = sM[j0]; cj = sC[j0];
-            mn = sM[j1]; cn = sC[j1];
+            mj = ldf(sM, j0); cj = ldf(sC, j0);
+            mn = ldf(sM, j1); cn = ldf(sC, j1);
         }
     }
     f2 dx[NP], dy[NP], dz[NP], rinv[NP], h2[NP];
@@ -218,8 +221,13 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
     JAcc32 J;
     J.x = J.y = J.z = J.p = 0ull;
     constexpr int kUnroll = SUB ? 2 : ((KID == NB_KERNEL_SPLINE) ? SYM_UNROLL_SPLINE : SYM_UNROLL);
-#pragma unroll kUnroll
-    for (int t = t0; t < t1; ++t) {
+    static_assert(32 % kUnroll == 0 && kUnroll >= 2, "chunks must tile a rotation round; records are fetched 2 steps ahead");
+    int lane_t4 = 4 * lane + 4 * t0;     // 4 (lane + tb), unmasked
+#pragma unroll 1
+    for (int tb = t0; tb < t1; tb += kUnroll, lane_t4 += 4 * kUnroll) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int t = tb + u;
         if (KID == NB_KERNEL_SPLINE && exact) {
             // exact step, in place (see sym_tile_f32_spline)
             float jx0, jx1, jy0, jy1, jz0, jz1, jp0, jp1;
@@ -299,7 +307,7 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
             J.z = shfl2(J.z, src);
         }
         if (MODE & NB_MODE_POT) J.p = shfl2(J.p, src);
-        if ((t & 31) == 31) {   // round complete: lane l holds the sums of particle (t - 31) + l
+        if (u == kUnroll - 1 && (tb & 31) == 32 - kUnroll) {   // round complete: lane l holds the sums of particle (t - 31) + l
             const int jb = t - 31;
             if (MODE & NB_MODE_FORCE) {
                 jw[0 * TJ + jb + lane] = sum2(J.x);
@@ -312,14 +320,20 @@ __device__ __forceinline__ void sym_tile_f32(const unsigned char* __restrict__ s
         // advance the record pipeline and prepare step t + 1 (the last iteration prepares a step that is not used)
         xj = xn; yj = yn; zj = zn; mj = mn; cj = cn;
         {
-            const int jn = rec_index((t + 2) & (TJ - 1));
-            xn = sX[jn]; yn = sY[jn]; zn = sZ[jn];
+            // step t + 2 = tb + kUnroll * ((u + 2) / kUnroll) + (u + 2) % kUnroll; tb is a multiple of kUnroll (<= 32), so
+            // the round bits of t + 2 are those of the chunk start
+            const int ua    = u + 2;
+            const int chunk = tb + (ua / kUnroll) * kUnroll;
+            const int jn    = (lane_t4 + 4 * ua) & 124;
+            const int gr    = chunk & (TJ - 32);          // uniform: folded into the base address
+            xn = ldf(sX + gr, jn); yn = ldf(sY + gr, jn); zn = ldf(sZ + gr, jn);
             if (!U) {
-                mn = sM[jn];
-                cn = sC[jn];
+                mn = ldf(sM + gr, jn);
+                cn = ldf(sC + gr, jn);
             }
         }
         prepare();
+      }
     }
 }
 
@@ -365,6 +379,8 @@ __device__ __forceinline__ void sym_tile_f32_spline(const unsigned char* __restr
         for (int s = 0; s < 32; ++s) {
             const float xj = xn, yj = yn, zj = zn, mj = mn, cj = cn;
             {
+                // (a running byte-offset counter as in sym_tile_f32 costs more MOVs than it saves address arithmetic in this
+                // non-unrolled loop: 97 against 91 instructions on the Newtonian path of a step)
                 const int jj = jb + ((lane + s + 1) & 31);   // s = 31 wraps to this lane's first record (unused)
                 xn = sX[jj];
                 yn = sY[jj];

@@ -19,6 +19,11 @@ from nbody_streams_b200 import build as B  # noqa: E402
 
 def main():
     name, flags = sys.argv[1], sys.argv[2:]
+    want = "sym_f64_kernel"
+    if "--show" in flags:                       # --show SUBSTRING: which kernels' register counts to print
+        k = flags.index("--show")
+        want = flags[k + 1]
+        del flags[k:k + 2]
     B.build()                                   # up-to-date objects of the unchanged units
     out = ROOT / "tmp_ab" / f"obj_{name}"
     out.mkdir(parents=True, exist_ok=True)
@@ -38,7 +43,6 @@ def main():
     lib = ROOT / "tmp_ab" / f"lib_{name}.so"
     subprocess.run([B._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib),
                     *map(str, keep + objs), "-lcudart"], check=True)
-    want = sys.argv[sys.argv.index("--show") + 1] if "--show" in sys.argv else "sym_f64_kernel"
     log = (out / "nb_sym_k1.ptxas.log").read_text() + (out / "nb_sym_k4.ptxas.log").read_text()
     for m in re.finditer(r"Compiling entry function '(\S+)'.*?\n.*?\n.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", log):
         fn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
