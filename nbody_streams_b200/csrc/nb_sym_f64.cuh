@@ -31,6 +31,13 @@ constexpr int SYM_STAGES_F64 = 2;                       // a tile takes ~40k cyc
 #define NB_SYM_UNROLL_F64 2
 #endif
 constexpr int SYM_UNROLL_F64 = NB_SYM_UNROLL_F64;       // rotation steps per loop iteration
+// force-only sweeps (18 FP64 instructions per pair, fewer live values) gain from 4 steps per iteration, the sweeps with the
+// potential do not (N = 262144, ms, 2 -> 4 steps: plummer force 44.55 -> 43.47, spline force 47.72 -> 47.39;
+// plummer force+potential 53.07 -> 53.49, spline force+potential 54.37 -> 54.30; profiles/r02_ubench_f64.md)
+#ifndef NB_SYM_UNROLL_F64_FORCE
+#define NB_SYM_UNROLL_F64_FORCE 4
+#endif
+constexpr int SYM_UNROLL_F64_FORCE = NB_SYM_UNROLL_F64_FORCE;
 
 __device__ __forceinline__ double shfl_d(const double v, const int src) {
     int lo = __double2loint(v), hi = __double2hiint(v);
@@ -122,7 +129,8 @@ __device__ __forceinline__ void sym_tile_f64(const unsigned char* __restrict__ s
     const double* __restrict__ sM = reinterpret_cast<const double*>(stage) + COMP_M * TJ;
     const double* __restrict__ sC = reinterpret_cast<const double*>(stage) + COMP_C * TJ;
     constexpr bool kUsesC = (KID == NB_KERNEL_PLUMMER || KID == NB_KERNEL_DEHNEN_K1 || KID == NB_KERNEL_DEHNEN_K2);
-    constexpr int kUnroll = SYM_UNROLL_F64;   // also for the spline (measured: +3 % force+potential, +7 % potential)
+    // (2 steps also for the spline: +3 % force+potential, +7 % potential over 1)
+    constexpr int kUnroll = (MODE == NB_MODE_FORCE) ? SYM_UNROLL_F64_FORCE : SYM_UNROLL_F64;
     const int src = (lane + 1) & 31;
 
 #pragma unroll 1
