@@ -49,7 +49,7 @@ sys.path.insert(0, str(ROOT))
 FLOPS_PER_INTERACTION = 20.0          # BASELINE.json convention
 print_json = None
 FP32_PEAK_NOMINAL_TF = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x lanes x 2 x max SM clock
-TRAFFIC_SYM_N1M = 319708416   # dram read + write bytes per launch of nb::sym_f32_kernel at N=1M (profiles/r02_ncu_sym_f32_bench_n1m.md)
+TRAFFIC_SYM_N1M = 391907328   # dram read + write bytes per launch of nb::sym_f32_kernel at N=1M (profiles/r02_ncu_sym_f32_bench_n1m.md)
 
 
 def parse():
