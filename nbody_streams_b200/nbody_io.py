@@ -196,9 +196,11 @@ class AsyncStateWriter:
             err, self.error = self.error, None
             raise err
 
-    def submit(self, kind: str, xv_dev, job) -> None:
+    def submit(self, kind: str, xv_dev, job, check: bool = True) -> None:
+        """`check=False`: do not raise a stored error here (multi-rank runs raise it on all ranks together)."""
         torch = self.torch
-        self.check()
+        if check:
+            self.check()
         buf = self.free.get()                       # back-pressure: at most two copies in flight
         cur = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)                # xv_dev was produced on the current stream

@@ -439,6 +439,28 @@ def run_nbody_gpu(
 
     writer = AsyncStateWriter(torch, eng.device, N) if (async_io and is_root) else None
 
+    class _WriteFailed(Exception):
+        """Several ranks: the root's verdict that a file write has failed, raised on EVERY rank at the same point."""
+
+        def __init__(self, error):
+            super().__init__(str(error))
+            self.error = error
+
+    def agree_on_io(err):
+        """Several ranks: only the root writes files, so only the root can see a write fail.  The root's status is
+        broadcast at every write event (all ranks call write_state at the same steps) and a failure is raised on
+        all of them — otherwise the root would leave the loop alone and the others would block in the next
+        collective.  `err`: the root's own exception, if any (ignored on the other ranks)."""
+        if is_root and err is None and writer is not None:
+            try:
+                writer.check()                    # a job queued at an earlier write event may have failed since
+            except BaseException as e:  # noqa: BLE001
+                err = e
+        msg = _root_says(None if (err is None or not is_root) else f"{type(err).__name__}: {err}")
+        if msg is not None:
+            raise _WriteFailed(err if (is_root and err is not None)
+                               else RuntimeError(f"file write failed on the root rank: {msg}"))
+
     def write_state(kind, counter, t, step):
         """Snapshot (kind='snapshot') or periodic restart (kind='restart') of the current state."""
         if kind == "snapshot":
@@ -448,21 +470,22 @@ def run_nbody_gpu(
         else:
             def job(xv_np, t=t, step=step, counter=counter):
                 _save_restart(xv_np, t, step, output_path, counter, **_restart_kwargs)
+        err = None
         if async_io:
             xv_dev = eng.state_device(root_only=True)     # only the writing rank receives the rows
             if is_root:
-                writer.submit(kind, xv_dev, job)
+                writer.submit(kind, xv_dev, job, check=(world == 1))
         else:
             xv_np = host_state()
             if is_root:
-                job(xv_np)
-
-    if snapshot_counter < len(snapshot_steps) and snapshot_steps[snapshot_counter] == start_step:
-        if save_snapshots:
-            write_state("snapshot", snapshot_counter, time, start_step)
-            if verbose:
-                print(f"Saved snapshot snap: {snapshot_counter:03d} at step {start_step}, time {time:.6e}...")
-        snapshot_counter += 1
+                try:
+                    job(xv_np)
+                except Exception as e:  # noqa: BLE001 - several ranks: raised on all of them by agree_on_io
+                    if world == 1:
+                        raise
+                    err = e
+        if world > 1:
+            agree_on_io(err)
 
     t_start = pytime.perf_counter()
     _report_every = max(1, remaining_steps // 20)
@@ -481,6 +504,13 @@ def run_nbody_gpu(
     loop_error = io_error = None
     steps_done = start_step
     try:
+        if snapshot_counter < len(snapshot_steps) and snapshot_steps[snapshot_counter] == start_step:
+            if save_snapshots:
+                write_state("snapshot", snapshot_counter, time, start_step)
+                if verbose:
+                    print(f"Saved snapshot snap: {snapshot_counter:03d} at step {start_step}, time {time:.6e}...")
+            snapshot_counter += 1
+
         for step_i in range(1, remaining_steps + 1):
             current_step = start_step + step_i
 
@@ -496,6 +526,7 @@ def run_nbody_gpu(
                 if hooks:                            # evaluated while the sweep runs
                     acc_ext = eval_hooks(current_step, time, force_extra is not None)
                 eng.kick(dt, acc_ext)                # half kick
+            steps_done = current_step                # the state is that of this step from here on
 
             while snapshot_counter < len(snapshot_steps) and current_step >= snapshot_steps[snapshot_counter]:
                 if save_snapshots:
@@ -530,8 +561,7 @@ def run_nbody_gpu(
 
             if current_step > 0 and (current_step % restart_interval) == 0:
                 write_state("restart", snapshot_counter, time, current_step)
-            steps_done = current_step
-            if writer is not None:
+            if writer is not None and world == 1:
                 try:
                     writer.check()
                 except BaseException as e:  # noqa: BLE001 - raised after the restart file is safe
@@ -546,6 +576,8 @@ def run_nbody_gpu(
                 write_state("snapshot", snapshot_counter, time, total_steps)
             snapshot_counter += 1
 
+    except _WriteFailed as e:           # several ranks: every rank arrives here at the same step
+        io_error = e.error
     except BaseException as e:  # noqa: BLE001 - re-raised below, once the writer thread is stopped
         loop_error = e
     if loop_error is not None:
@@ -559,7 +591,17 @@ def run_nbody_gpu(
         except BaseException as e:  # noqa: BLE001
             io_error = io_error or e
     if is_root:
-        _save_restart(xv_final_cpu, time, steps_done, output_path, snapshot_counter, **_restart_kwargs)
+        try:
+            _save_restart(xv_final_cpu, time, steps_done, output_path, snapshot_counter, **_restart_kwargs)
+        except Exception as e:  # noqa: BLE001
+            if world == 1 or io_error is not None:
+                raise
+            io_error = e
+    if world > 1:
+        # the outcome of the run is the root's: a write that failed at the very end is raised on every rank too
+        msg = _root_says(None if (io_error is None or not is_root) else f"{type(io_error).__name__}: {io_error}")
+        if msg is not None and io_error is None:
+            io_error = RuntimeError(f"file write failed on the root rank: {msg}")
     if io_error is not None:
         raise io_error
 

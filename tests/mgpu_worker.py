@@ -165,6 +165,38 @@ def main():
     msgs.append(f"unbinding: bound {int(b1.sum())}/7000, sharded equal {np.array_equal(b1, bw)}")
     ok &= bool(np.array_equal(b1, bw)) and bool(np.allclose(c1, cw, rtol=1e-12)) and 0 < b1.sum() < 7000
 
+    # a file write that fails on the root (the only rank that writes) must stop EVERY rank at the same step — not
+    # leave the others blocked in the next collective — and restart.npz must hold that step (async and synchronous I/O)
+    import nbody_streams_b200.run as run_mod
+
+    real_save = run_mod._save_restart
+    for async_io in (True, False):
+        calls = {"n": 0}
+
+        def flaky(xv_np, t, step, *a, **k):
+            calls["n"] += 1
+            if calls["n"] == 1:
+                raise OSError("No space left on device (simulated)")
+            return real_save(xv_np, t, step, *a, **k)
+
+        run_mod._save_restart = flaky
+        raised, fdir = None, out / f"iofail_{int(async_io)}"
+        try:
+            nb.run_nbody_gpu(xv, mass, 0.0, 40 * 1e-4, 1e-4, h, output_dir=str(fdir), group=dist.group.WORLD,
+                             precision="float64", kernel="spline", save_snapshots=False, verbose=False,
+                             restart_interval=5, async_io=async_io)
+        except (OSError, RuntimeError) as e:
+            raised = e
+        finally:
+            run_mod._save_restart = real_save
+        dist.barrier()
+        stopped = int(np.load(fdir / "restart.npz")["step"])
+        good = raised is not None and "simulated" in str(raised) and 5 <= stopped < 40 and stopped % 5 == 0
+        good &= isinstance(raised, OSError) if rank == 0 else isinstance(raised, RuntimeError)
+        msgs.append(f"root write failure (async_io={async_io}): every rank raised, stopped at step {stopped} "
+                    f"(rank {rank}: {type(raised).__name__})")
+        ok &= bool(good)
+
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
