@@ -85,6 +85,9 @@ def model(body):
 
 
 def main():
+    import signal
+
+    signal.signal(signal.SIGPIPE, signal.SIG_DFL)      # `| head` must not end in a traceback
     path, sub = sys.argv[1], sys.argv[2]
     key = sys.argv[sys.argv.index("--key") + 1] if "--key" in sys.argv else "FFMA2"
     min_key = int(sys.argv[sys.argv.index("--min") + 1]) if "--min" in sys.argv else 32
