@@ -203,3 +203,58 @@ def test_symmetric_partial_sums_reduce_scatter_world2():
         assert p.exitcode == 0
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+# ---------------------------------------------------------------------------
+# staging-free row gather (engine.gather_rows_padded): what the fields API (gather='all' / 'root') and the
+# root-only state gather of run_nbody_gpu's writer use
+# ---------------------------------------------------------------------------
+from nbody_streams_b200.engine import gather_rows_padded  # noqa: E402
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        for n in (700, 513, 256, 3):        # ragged shards, a rank with one tile of padding only (n <= 256), tiny n
+            L = ShardLayout(n, world)
+            full = torch.arange(n * 3, dtype=torch.float64).reshape(n, 3) + 0.5
+            rows = L.rows(rank)
+            padded = torch.full((L.shard, 3), -1.0, dtype=torch.float64)   # padding rows must never show up
+            padded[: L.count(rank)] = full[rows]
+            got = gather_rows_padded(padded, L, rank)
+            ok &= bool(torch.equal(got, full))
+            local = padded[: L.count(rank)]
+            got_root = gather_rows_padded(padded, L, rank, root_only=True, local=local)
+            ok &= bool(torch.equal(got_root, full)) if rank == 0 else (got_root is local)
+            vec = torch.full((L.shard,), -1.0, dtype=torch.float64)        # 1-D rows (phi)
+            vec[: L.count(rank)] = full[rows, 0]
+            ok &= bool(torch.equal(gather_rows_padded(vec, L, rank), full[:, 0]))
+        flag = torch.tensor([1.0 if ok else 0.0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            out.put(bool(flag.item() == 1.0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gather_rows_padded_world2_all_and_root_only():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=100)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert res is True
+
+
+def test_gather_rows_padded_world1_drops_the_padding():
+    L = ShardLayout(300, 1)
+    padded = torch.zeros((L.shard, 3))
+    assert L.shard == 512 and gather_rows_padded(padded, L, 0).shape == (300, 3)
