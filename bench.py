@@ -22,6 +22,9 @@ The JSON line carries, besides the driver contract keys:
                 FFMA peak measured in the same process by nb_ubench (MEASURED_PEAKS.json has no FP32 figure);
   cpu_baseline  the oracle port of the reference's Numba path timed on this box's host cores on a bounded
                 row sample of the same workload (N = 1 only);
+  cpu_baseline_numba  the same sample through oracle/numba_port.py — the reference's CPU path restated in its own
+                technology (Numba @njit(parallel=True); bit-identical to and as fast as the reference's functions
+                where both can run, BASELINE.md 2) — in a subprocess; {"unavailable": ...} when Numba is missing;
   e2e           the same metric through the public host-array API (compute_nbody_forces_potential_gpu with
                 NumPy in / NumPy out): H2D of positions and D2H of acc+phi inside the timed region;
   parity        outside the timed region: acc and phi of rank 0's first rows after the last step against the
@@ -72,6 +75,7 @@ def parse():
                    help="N>1: NCCL all-gather of the j-records, or the exchange fused into the drift kernel (NVLink stores)")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     p.add_argument("--skip-cpu", action="store_true")
+    p.add_argument("--skip-numba", action="store_true", help="no cpu_baseline_numba key (Numba restatement in a subprocess)")
     p.add_argument("--skip-e2e", action="store_true")
     return p.parse_args()
 
@@ -170,6 +174,25 @@ def cpu_sample(args, xv, m, seconds: float) -> dict:
             "seconds": t, "rows": rows}
 
 
+def numba_sample(args, seconds: float) -> dict:
+    """The reference's CPU path in its own technology: oracle/numba_port.py (a Numba @njit(parallel=True) restatement,
+    bit-identical to and as fast as the reference's functions in the build container) on a bounded row
+    sample, in a SUBPROCESS — a missing or misbehaving Numba on the box can only cost this one key."""
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "NUMBA_NUM_THREADS")}
+    env.setdefault("NUMBA_CACHE_DIR", "/tmp/nbody_b200_numba_cache")
+    cmd = [sys.executable, "-m", "oracle.numba_port", "--n", str(args.n), "--kernel", args.kernel,
+           "--precision", "float64" if args.precision == "float64" else "float32",
+           "--softening", str(args.softening), "--seconds", str(seconds),
+           "--threads", str(len(os.sched_getaffinity(0)))]
+    try:
+        r = subprocess.run(cmd, cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=60 + 6 * seconds)
+        if r.returncode != 0:
+            return {"unavailable": (r.stderr.strip().splitlines() or ["non-zero exit"])[-1][:200]}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001 - optional key
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -200,6 +223,8 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.skip_numba:
+        line["cpu_baseline_numba"] = numba_sample(args, min(args.cpu_seconds, 5.0))
     print_json(line)
 
 
@@ -479,6 +504,9 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_sample(args, xv, m, args.cpu_seconds)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    cpu_numba = None
+    if rank == 0 and world == 1 and not args.skip_cpu and not args.skip_numba:
+        cpu_numba = numba_sample(args, min(args.cpu_seconds, 5.0))
 
     if rank == 0:
         line = {
@@ -505,6 +533,8 @@ def main():
             "parity": parity, "other_sweeps": sweeps, "ref_gpu_kernel": ref_gpu,
             "clocks": clocks,
         }
+        if cpu_numba is not None:
+            line["cpu_baseline_numba"] = cpu_numba
         print_json(line)
     if world > 1:
         dist.destroy_process_group()

@@ -119,3 +119,33 @@ def test_error_paths():
         oracle.compute_nbody_forces_cpu(pos, 1.0, kernel="nope")
     with pytest.raises(ValueError):
         oracle.compute_nbody_forces_cpu(pos, 1.0, precision="float16")
+
+
+# ---- the Numba restatement (oracle/numba_port.py: bench.py's cpu_baseline_numba) against the C oracle --------------
+
+@pytest.mark.parametrize("precision,tol", [("float64", 1e-13), ("float32", 2e-6)])
+def test_numba_port_matches_the_c_oracle(precision, tol):
+    """Same arithmetic and typing as oracle/nbody_oracle.c (which the tests above pin to the reference's own
+    outputs); tools/numba_vs_reference.py additionally shows bit-identical results and equal speed against the
+    imported reference in the build container."""
+    pytest.importorskip("numba")
+    from oracle import numba_port as P
+
+    rng = np.random.default_rng(11)
+    n = 301
+    pos = rng.normal(size=(n, 3))
+    mass = rng.uniform(0.5, 1.5, n)
+    h = rng.uniform(0.01, 0.5, n)
+    G = 4.300917270069976e-06
+    for kernel in ("newtonian", "plummer", "dehnen_k1", "dehnen_k2", "spline"):
+        a = P.compute_nbody_forces_numba(pos, mass, h, G, kernel, precision)
+        p = P.compute_nbody_potential_numba(pos, mass, h, G, kernel, precision)
+        a_c = oracle.compute_nbody_forces_cpu(pos, mass, h, G, kernel, precision=precision)
+        p_c = oracle.compute_nbody_potential_cpu(pos, mass, h, G, kernel, precision=precision)
+        assert a.dtype == a_c.dtype and p.dtype == p_c.dtype
+        assert np.abs(a - a_c).max() / np.abs(a_c).max() <= tol, kernel
+        assert np.abs(p - p_c).max() / np.abs(p_c).max() <= tol, kernel
+    rows = (100, 164)                                      # a row range is exact (independent per i)
+    a = P.compute_nbody_forces_numba(pos, mass, h, G, "spline", precision, rows=rows)
+    full = P.compute_nbody_forces_numba(pos, mass, h, G, "spline", precision)
+    assert np.array_equal(a, full[rows[0]:rows[1]])
