@@ -183,6 +183,14 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.SIGNATURES) <= declared
 
 
+def test_integration_guide_covers_every_entry_point():
+    """INTEGRATION.md shows the reference-side binding; every symbol of the header must be accounted for there."""
+    header = (ROOT / "include" / "nbody_sm100.h").read_text()
+    guide = (ROOT / "INTEGRATION.md").read_text()
+    for name in sorted(set(re.findall(r"\b(nb_[a-z0-9_]+)\s*\(", header))):
+        assert name in guide, f"{name} is declared in include/nbody_sm100.h but not mentioned in INTEGRATION.md"
+
+
 def test_library_host_side_queries():
     lib = _lib.load()
     assert lib.nb_version() >= 100
