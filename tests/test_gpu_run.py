@@ -254,7 +254,7 @@ def test_host_potential_overlaps_the_sweep(nb, tmp_path):
             time.sleep(0.004)                  # stands for agama's CPU evaluation
             return -0.5 * np.asarray(pos)
 
-    N, steps = 200_000, 6                       # sweep ~10 ms per step > hook 4 ms + copies
+    N, steps = 300_000, 6                       # sweep ~24 ms per step >> hook 4 ms + copies (margin for a loaded host)
     xv, m = nb.make_plummer_sphere(N, M_total=1e9, a=1.0, seed=3)
     tl = []
     out = nb.run_nbody_gpu(xv, m, 0.0, steps * 1e-4, 1e-4, 0.05, precision="float32", kernel="plummer",
